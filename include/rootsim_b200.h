@@ -1,0 +1,172 @@
+/*
+ * rootsim_b200.h -- C-ABI of the B200-native Time Warp engine (the drop-in boundary).
+ *
+ * One shared library is produced per model by `rootsim-cc` (lib<model>.so): the model's unmodified
+ * C sources, compiled as __device__ callbacks, fused with the engine kernels (sm_100a).  The host
+ * runtime (host/rs_main.c, plain C, ROOT-Sim compatible CLI) and any foreign-language binding talk
+ * to it ONLY through the entry points below: plain pointers and sizes, no CUDA or torch types.
+ * There is no CPU execution path behind this ABI: without a usable CUDA device rs_dev_init fails
+ * with RS_ERR_NO_DEVICE.
+ *
+ * Each entry point names the reference interface it stands in for (paths relative to the
+ * HPDCS/ROOT-Sim 2.0.0 tree).
+ */
+#ifndef ROOTSIM_B200_H
+#define ROOTSIM_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_ABI_VERSION 1
+
+/* error codes (reference: rootsim_error(fatal=true) -> exit(EXIT_FAILURE), src/core/core.c:220-250) */
+enum {
+	RS_OK = 0,
+	RS_ERR_NO_DEVICE = 1,		/* no CUDA device / driver: the product has no CPU fallback        */
+	RS_ERR_BAD_CONFIG = 2,
+	RS_ERR_OOM = 3,
+	RS_ERR_CUDA = 4,
+	RS_ERR_MODEL = 5,		/* model raised a fatal condition, see rs_dev_error() / status bits  */
+	RS_ERR_CAPACITY = 6		/* a device-side pool overflowed, see status bits                    */
+};
+
+/* device status bits (rs_stats_t.status); the first three are the reference's three send-time checks
+ * (src/communication/communication.c:280-294) */
+#define RS_ST_BAD_RECEIVER	0x0001u	/* receiver >= n_prc_tot: warned and dropped (not fatal)        */
+#define RS_ST_PAST_EVENT	0x0002u	/* timestamp < now: fatal                                       */
+#define RS_ST_RESERVED_TYPE	0x0004u	/* event type >= 65532: fatal                                   */
+#define RS_ST_MODEL_EXIT	0x0008u	/* model called exit()/abort()                                  */
+#define RS_ST_ARENA_FULL	0x0010u	/* per-LP state arena exhausted (malloc returned NULL)           */
+#define RS_ST_POOL_FULL		0x0020u	/* pending-event pool exhausted                                 */
+#define RS_ST_WINDOW_FULL	0x0040u	/* window/grouping buffer exhausted                             */
+#define RS_ST_OUT_FULL		0x0080u	/* per-window output (sent-log) buffer exhausted                */
+#define RS_ST_HORIZON		0x0100u	/* event beyond the calendar horizon (n_buckets*bucket_width)   */
+#define RS_ST_LATE_FULL		0x0200u	/* too many in-window arrivals for one LP                       */
+#define RS_ST_PAYLOAD		0x0400u	/* event payload larger than max_payload                        */
+#define RS_ST_NO_EVENTS		0x0800u	/* pending set became empty before the horizon                  */
+#define RS_ST_FATAL_MASK	(RS_ST_PAST_EVENT | RS_ST_RESERVED_TYPE | RS_ST_MODEL_EXIT | RS_ST_ARENA_FULL | \
+				 RS_ST_POOL_FULL | RS_ST_WINDOW_FULL | RS_ST_OUT_FULL | RS_ST_HORIZON | RS_ST_LATE_FULL | RS_ST_PAYLOAD)
+
+/* engine flags */
+#define RS_F_TRACE		0x1u	/* keep the per-LP committed-trace digest (count/hash/last ts)   */
+
+/*
+ * Run configuration.  Mirrors the fields of the reference's `rootsim_config` that matter on this
+ * path (src/core/init.h:57-80, defaults src/core/init.c:315-340) plus the sizing of the device pools.
+ * Zero in a sizing field selects the engine default.
+ */
+typedef struct rs_config {
+	uint32_t abi_version;		/* RS_ABI_VERSION                                                  */
+	uint32_t n_lps;			/* --lp: total LPs in the simulation (all ranks)                   */
+	uint32_t lp_first;		/* first global LP id owned by this engine (block partition,       */
+	uint32_t lp_count;		/*   src/core/core.c:275-300); lp_count==0 means all n_lps        */
+	uint64_t master_seed;		/* ~/.rootsim/numerical.conf value (src/lib/numerical.c:326-391)   */
+	double simulation_time;		/* --simulation-time; 0 = run until OnGVT says stop                */
+	uint32_t ckpt_period;		/* --p (accepted; checkpoints are taken per LP per window)         */
+	uint32_t gvt_snapshot_cycles;	/* --gvt-snapshot-cycles: OnGVT termination check every N windows  */
+	double bucket_width;		/* calendar bucket width in simulated time (power of two)          */
+	uint32_t n_buckets;		/* calendar ring size (power of two)                               */
+	uint32_t window_events;		/* target number of events per optimistic window                   */
+	uint32_t arena_bytes;		/* per-LP state arena (model malloc heap), multiple of 16          */
+	uint32_t max_payload;		/* largest event payload in bytes                                  */
+	uint32_t flags;			/* RS_F_*                                                          */
+	uint64_t max_pending;		/* capacity of the pending-event pool (events)                     */
+	uint32_t max_window;		/* capacity of the per-window grouping buffer (events)             */
+	uint32_t max_out;		/* capacity of the per-window output buffer (events)               */
+	int32_t device;			/* CUDA device ordinal                                             */
+	uint32_t topology_geometry;	/* filled from the model's topology_settings by rs_model_info()    */
+	uint32_t topology_out_of;	/*   .out_of_topology                                              */
+	uint32_t reserved[6];
+} rs_config_t;
+
+/* Aggregate counters; definitions follow src/statistics/statistics.h:87-103 and :345-349. */
+typedef struct rs_stats {
+	uint64_t committed_events;	/* STAT_COMMITTED                                                  */
+	uint64_t executed_events;	/* STAT_EVENT (every non-silent execution, rolled back ones too)   */
+	uint64_t silent_events;		/* STAT_SILENT: coast-forward re-executions                        */
+	uint64_t rollbacks;		/* STAT_ROLLBACK                                                   */
+	uint64_t antimessages;		/* STAT_ANTIMESSAGE                                                */
+	uint64_t checkpoints;		/* STAT_CKPT                                                       */
+	uint64_t checkpoint_bytes;	/* STAT_CKPT_MEM                                                   */
+	uint64_t windows;		/* GVT rounds                                                      */
+	uint64_t relax_rounds;		/* in-window straggler rounds                                      */
+	uint64_t late_events;		/* events delivered inside the window they were sent in           */
+	uint64_t pending_events;	/* events still in the calendar                                    */
+	uint64_t peak_window_events;
+	double gvt;			/* last committed GVT (get_last_gvt(), src/gvt/gvt.c)              */
+	double loop_seconds;		/* wall time of rs_dev_run loops (statistics_start..stop)          */
+	double device_seconds;		/* CUDA-event time of rs_dev_run loops                             */
+	uint32_t status;		/* RS_ST_* bits                                                    */
+	uint32_t all_lps_agree;		/* last OnGVT AND-reduction (src/gvt/ccgs.c:64-84)                 */
+	uint64_t kernel_launches;	/* engine kernels launched so far                                  */
+	uint64_t reserved[4];
+} rs_stats_t;
+
+/* Per-LP committed-trace digest (test/diagnostic interface; same definition as the reference-side
+ * tracing shim in oracle/trace_shim.c): events with timestamp < simulation_time, in commit order. */
+typedef struct rs_lp_trace {
+	uint64_t count;			/* committed events of this LP                                     */
+	uint64_t hash;			/* FNV-1a-64 over (timestamp bits, int32 type) of those events     */
+	double last_ts;			/* timestamp of the last committed event                           */
+	uint64_t seed;			/* RNG seed after it (numerical_state_t.seed)                      */
+} rs_lp_trace_t;
+
+typedef struct rs_model_info {
+	const void *model_argp;		/* struct argp* of the model or NULL (src/ROOT-Sim.h:67-69)        */
+	int32_t has_topology;		/* model defines topology_settings                                 */
+	uint32_t topology_type;
+	uint32_t topology_geometry;
+	uint32_t topology_out_of;
+	const char *topology_path;
+	const char *engine;		/* "cuda-sm100a" (product) or "emu" (test-only build)              */
+} rs_model_info_t;
+
+typedef struct rs_engine rs_engine_t;
+
+/* What the model linked into this library declares.  Replaces the weak-symbol probing of
+ * src/core/init.c:385-390 (model_argp) and src/lib/topology/topology.c:210-214 (topology_settings). */
+void rs_model_info(rs_model_info_t *out);
+
+/* Fill cfg with the defaults of the reference CLI (src/core/init.c:315-340) and of the engine. */
+void rs_config_defaults(rs_config_t *cfg);
+
+/* Per-LP seed derivation on the host: seeds[i] for global LP id lp_first+i.
+ * Replaces numerical_init (src/lib/numerical.c:399-411) incl. sanitize_seed (:263-312). */
+void rs_host_lp_seeds(uint64_t master_seed, uint32_t lp_first, uint32_t lp_count, uint64_t *seeds);
+
+/* Create the device engine: allocate the LP table, state arenas, checkpoint store, calendar and
+ * window buffers in HBM, copy the per-LP seeds (HOST buffer, lp_count entries; NULL = derive from
+ * cfg->master_seed), and run INIT on every LP.  Replaces the parallel branch of SystemInit
+ * (src/core/init.c:434-453) and initialize_worker_thread's INIT bootstrap (src/scheduler/scheduler.c:202-244). */
+int rs_dev_init(const rs_config_t *cfg, const uint64_t *host_seeds, rs_engine_t **out);
+
+/* Advance the simulation by at most max_windows optimistic windows (0 = until termination).
+ * One window = select -> group -> execute -> straggler rounds (rollback, coast-forward, cancel) ->
+ * commit (GVT, fossil collection).  Replaces the body of main_simulation_loop
+ * (src/main.c:132-170: process_bottom_halves, schedule, gvt_operations).
+ * Returns RS_OK and sets *finished (may be NULL) when end_computing() (src/main.c:67-87) holds. */
+int rs_dev_run(rs_engine_t *e, uint64_t max_windows, int *finished);
+
+/* Counters (replaces statistics_stop's aggregation, src/statistics/statistics.c:442-568). */
+int rs_dev_stats(rs_engine_t *e, rs_stats_t *out);
+
+/* Copy n per-LP digests / committed-event counts / first `bytes` bytes of each LP's model state
+ * to HOST buffers (per-LP statistics of src/statistics/statistics.c:660-733). */
+int rs_dev_trace(rs_engine_t *e, rs_lp_trace_t *out, uint32_t n);
+int rs_dev_lp_state(rs_engine_t *e, void *out, uint32_t bytes_per_lp, uint32_t n);
+
+/* Multi-GPU plumbing (one engine per GPU; see DESIGN.md "multi-GPU"): buffers are device pointers
+ * owned by the engine, exchanged by the caller (NCCL) between the phases of a window. */
+int rs_dev_exchange_info(rs_engine_t *e, void **outbox, uint64_t **outbox_counts, void **inbox, uint32_t *record_bytes, uint64_t *capacity);
+
+const char *rs_dev_error(rs_engine_t *e);
+int rs_dev_fini(rs_engine_t *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -25,7 +25,7 @@
 #include <argp.h>
 
 #ifdef RS_DEVICE_BUILD
-#define RS_API __device__
+#define RS_API __host__ __device__
 #else
 #define RS_API
 #endif

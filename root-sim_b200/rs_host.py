@@ -1,0 +1,215 @@
+"""ctypes binding of the C-ABI in include/rootsim_b200.h (host-side harness for tests and bench.py).
+
+The reference is compiled C and so is this project's host runtime (host/rs_main.c); this module is
+only the thin foreign-function stub a Python tool needs: it mirrors the structs of the header
+field by field and adds no logic of its own.  Every call goes to lib<model>.so produced by
+bin/rootsim-cc (CUDA, sm_100a).  There is no CPU path: on a machine without a GPU
+`Engine.init` raises RsError(RS_ERR_NO_DEVICE).
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+BUILT = os.path.join(HERE, "_built")
+ROOTSIM_CC = os.path.join(HERE, "bin", "rootsim-cc")
+
+RS_ABI_VERSION = 1
+RS_F_TRACE = 0x1
+
+STATUS_BITS = {
+    0x0001: "BAD_RECEIVER", 0x0002: "PAST_EVENT", 0x0004: "RESERVED_TYPE", 0x0008: "MODEL_EXIT",
+    0x0010: "ARENA_FULL", 0x0020: "POOL_FULL", 0x0040: "WINDOW_FULL", 0x0080: "OUT_FULL",
+    0x0100: "HORIZON", 0x0200: "LATE_FULL", 0x0400: "PAYLOAD", 0x0800: "NO_EVENTS",
+}
+ERRORS = {0: "RS_OK", 1: "RS_ERR_NO_DEVICE", 2: "RS_ERR_BAD_CONFIG", 3: "RS_ERR_OOM", 4: "RS_ERR_CUDA",
+          5: "RS_ERR_MODEL", 6: "RS_ERR_CAPACITY"}
+
+
+class RsError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "?"), code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("n_lps", C.c_uint32), ("lp_first", C.c_uint32), ("lp_count", C.c_uint32),
+        ("master_seed", C.c_uint64), ("simulation_time", C.c_double),
+        ("ckpt_period", C.c_uint32), ("gvt_snapshot_cycles", C.c_uint32),
+        ("bucket_width", C.c_double), ("n_buckets", C.c_uint32), ("window_events", C.c_uint32),
+        ("arena_bytes", C.c_uint32), ("max_payload", C.c_uint32), ("flags", C.c_uint32),
+        ("max_pending", C.c_uint64), ("max_window", C.c_uint32), ("max_out", C.c_uint32),
+        ("device", C.c_int32), ("topology_geometry", C.c_uint32), ("topology_out_of", C.c_uint32),
+        ("reserved", C.c_uint32 * 6),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("committed_events", C.c_uint64), ("executed_events", C.c_uint64), ("silent_events", C.c_uint64),
+        ("rollbacks", C.c_uint64), ("antimessages", C.c_uint64), ("checkpoints", C.c_uint64),
+        ("checkpoint_bytes", C.c_uint64), ("windows", C.c_uint64), ("relax_rounds", C.c_uint64),
+        ("late_events", C.c_uint64), ("pending_events", C.c_uint64), ("peak_window_events", C.c_uint64),
+        ("gvt", C.c_double), ("loop_seconds", C.c_double), ("device_seconds", C.c_double),
+        ("status", C.c_uint32), ("all_lps_agree", C.c_uint32), ("kernel_launches", C.c_uint64),
+        ("reserved", C.c_uint64 * 4),
+    ]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d["status_names"] = [n for b, n in STATUS_BITS.items() if self.status & b]
+        return d
+
+
+class LpTrace(C.Structure):
+    _fields_ = [("count", C.c_uint64), ("hash", C.c_uint64), ("last_ts", C.c_double), ("seed", C.c_uint64)]
+
+
+class ModelInfo(C.Structure):
+    _fields_ = [("model_argp", C.c_void_p), ("has_topology", C.c_int32), ("topology_type", C.c_uint32),
+                ("topology_geometry", C.c_uint32), ("topology_out_of", C.c_uint32),
+                ("topology_path", C.c_char_p), ("engine", C.c_char_p)]
+
+
+EXPORTS = ["rs_model_info", "rs_config_defaults", "rs_host_lp_seeds", "rs_dev_init", "rs_dev_run", "rs_dev_stats",
+           "rs_dev_trace", "rs_dev_lp_state", "rs_dev_exchange_info", "rs_dev_error", "rs_dev_fini"]
+
+
+def load(path):
+    lib = C.CDLL(path)
+    lib.rs_model_info.argtypes = [C.POINTER(ModelInfo)]
+    lib.rs_model_info.restype = None
+    lib.rs_config_defaults.argtypes = [C.POINTER(Config)]
+    lib.rs_config_defaults.restype = None
+    lib.rs_host_lp_seeds.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+    lib.rs_host_lp_seeds.restype = None
+    lib.rs_dev_init.argtypes = [C.POINTER(Config), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
+    lib.rs_dev_init.restype = C.c_int
+    lib.rs_dev_run.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
+    lib.rs_dev_run.restype = C.c_int
+    lib.rs_dev_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.rs_dev_stats.restype = C.c_int
+    lib.rs_dev_trace.argtypes = [C.c_void_p, C.POINTER(LpTrace), C.c_uint32]
+    lib.rs_dev_trace.restype = C.c_int
+    lib.rs_dev_lp_state.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    lib.rs_dev_lp_state.restype = C.c_int
+    lib.rs_dev_error.argtypes = [C.c_void_p]
+    lib.rs_dev_error.restype = C.c_char_p
+    lib.rs_dev_fini.argtypes = [C.c_void_p]
+    lib.rs_dev_fini.restype = C.c_int
+    return lib
+
+
+class Engine:
+    """One device engine (one GPU, one block of LPs)."""
+
+    def __init__(self, lib_path):
+        self.lib = load(lib_path)
+        self.h = C.c_void_p()
+        self.cfg = Config()
+        self.lib.rs_config_defaults(C.byref(self.cfg))
+
+    def info(self):
+        mi = ModelInfo()
+        self.lib.rs_model_info(C.byref(mi))
+        return mi
+
+    def init(self, host_seeds=None, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.cfg, k):
+                raise KeyError(k)
+            setattr(self.cfg, k, v)
+        seeds = None
+        if host_seeds is not None:
+            seeds = host_seeds if isinstance(host_seeds, C.Array) else (C.c_uint64 * len(host_seeds))(*host_seeds)
+        rc = self.lib.rs_dev_init(C.byref(self.cfg), seeds, C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.rs_dev_error(self.h).decode() if self.h else ""
+            self.fini()
+            raise RsError(rc, msg)
+        return self
+
+    def run(self, max_windows=0):
+        fin = C.c_int(0)
+        rc = self.lib.rs_dev_run(self.h, max_windows, C.byref(fin))
+        if rc != 0:
+            raise RsError(rc, self.lib.rs_dev_error(self.h).decode())
+        return bool(fin.value)
+
+    def stats(self):
+        st = Stats()
+        self.lib.rs_dev_stats(self.h, C.byref(st))
+        return st
+
+    def trace(self, n=None):
+        n = n or (self.cfg.lp_count or self.cfg.n_lps)
+        arr = (LpTrace * n)()
+        rc = self.lib.rs_dev_trace(self.h, arr, n)
+        if rc != 0:
+            raise RsError(rc, "trace")
+        return arr
+
+    def lp_state(self, nbytes, n=None):
+        n = n or (self.cfg.lp_count or self.cfg.n_lps)
+        buf = (C.c_ubyte * (nbytes * n))()
+        rc = self.lib.rs_dev_lp_state(self.h, buf, nbytes, n)
+        if rc != 0:
+            raise RsError(rc, "lp_state")
+        return bytes(buf)
+
+    def fini(self):
+        if self.h:
+            self.lib.rs_dev_fini(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.fini()
+
+
+def lp_seeds(lib, master_seed, lp_first, lp_count):
+    arr = (C.c_uint64 * lp_count)()
+    lib.rs_host_lp_seeds(master_seed, lp_first, lp_count, arr)
+    return arr
+
+
+def model_sources(name):
+    """Sources of a model by name: the repo's own tests/models/<name>, else the reference's
+    models/<name> when the reference tree is present (this container only)."""
+    own = os.path.join(REPO, "tests", "models", name)
+    ref = os.path.join(os.environ.get("RS_REFERENCE", "/root/reference"), "models", name)
+    for d in (own, ref):
+        if os.path.isdir(d):
+            return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".c"))
+    return []
+
+
+def lib_path(name, emu=False):
+    return os.path.join(BUILT, "lib%s%s.so" % (name, "_emu" if emu else ""))
+
+
+def build_model(name, emu=False, force=False, extra=()):
+    """Compile a model with rootsim-cc into root-sim_b200/_built/.  Returns the library path, or the
+    prebuilt library when the sources are not available (GPU box: no /root/reference)."""
+    out = lib_path(name, emu)
+    srcs = model_sources(name)
+    if not srcs:
+        if os.path.exists(out):
+            return out
+        raise FileNotFoundError("no sources and no prebuilt library for model %r" % name)
+    deps = srcs + [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + \
+        [os.path.join(HERE, "include", f) for f in os.listdir(os.path.join(HERE, "include"))] + \
+        [ROOTSIM_CC, os.path.join(REPO, "include", "rootsim_b200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    os.makedirs(BUILT, exist_ok=True)
+    cmd = [sys.executable, ROOTSIM_CC, "--shared"] + (["--emu"] if emu else []) + list(extra) + srcs + ["-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("rootsim-cc failed:\n" + r.stdout + r.stderr)
+    return out
