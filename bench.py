@@ -1,0 +1,241 @@
+#!/usr/bin/env python3
+"""bench.py -- committed events/sec of the B200-native Time Warp engine on PHOLD.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--lps L] [--sim-time T]
+
+One STEP = one complete bounded-horizon PHOLD run (BASELINE.json configs[1]: models/phold,
+1,048,576 LPs, exponential timestamp increment, --simulation-time T, master seed 12345678901234567):
+the engine is created and INIT is run on every LP OUTSIDE the timed region (inputs resident in HBM),
+the timed region is the event loop (rs_dev_run to the horizon), timed on the device with CUDA events
+recorded by the engine on its own stream.  `value` = committed events of K steps / their device time.
+`e2e` = the same metric through the C-ABI with HOST buffers: per-LP seeds copied host->device, engine
+creation, INIT, the event loop, and the per-LP committed-event digests copied device->host, all inside
+a wall-clock timed region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "root-sim_b200"))
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+MASTER_SEED = 12345678901234567
+B_ALG_PHOLD = 274.0          # algorithmic bytes per committed event, SURVEY.md section 8(d) / DESIGN.md
+METRIC = "committed events/sec (PHOLD 1M LPs)"
+
+
+def measured_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+        self.index = index
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split("\n")[0]
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def phold_cfg(n_lps, sim_time):
+    """Pool sizing for shipped PHOLD (population grows ~ N*0.9*e^{0.04 t})."""
+    import math
+    pending = int(n_lps * (1.0 * math.exp(0.04 * sim_time) + 1.0) * 1.25) + (1 << 20)
+    rate = n_lps * 0.2 * math.exp(0.04 * sim_time)           # events per unit of simulated time at the end
+    bw = 0.0625
+    while rate * bw > 1.5e6 and bw > 1.0 / 1024:
+        bw /= 2
+    return dict(n_lps=n_lps, master_seed=MASTER_SEED, simulation_time=float(sim_time), window_events=1 << 21,
+                arena_bytes=128, max_pending=pending, bucket_width=bw, n_buckets=max(4096, int(160 / bw)),
+                gvt_snapshot_cycles=1 << 30, flags=0)
+
+
+def run_ours(args):
+    import rs_host
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib_path = rs_host.build_model("phold")
+    n_lps, T = args.lps, args.sim_time
+    cfg = phold_cfg(n_lps, T)
+    cfg["device"] = local
+    lib = rs_host.load(lib_path)
+    seeds = rs_host.lp_seeds(lib, MASTER_SEED, 0, n_lps)
+
+    def one_step(e2e):
+        t0 = time.perf_counter()
+        eng = rs_host.Engine(lib_path)
+        eng.init(host_seeds=seeds if e2e else None, **cfg)
+        fin = eng.run()
+        st = eng.stats()
+        tr = eng.trace() if e2e else None
+        t1 = time.perf_counter()
+        assert fin and (st.status & ~0x1) == 0, st.as_dict()
+        committed = st.committed_events - n_lps       # INIT events are processed at engine creation
+        res = dict(committed=committed, device_s=st.device_seconds, wall_s=t1 - t0, launches=st.kernel_launches,
+                   windows=st.windows, rollbacks=st.rollbacks, executed=st.executed_events, silent=st.silent_events,
+                   rounds=st.relax_rounds, late=st.late_events, antimessages=st.antimessages)
+        if e2e:
+            res["count_sum"] = sum(tr[i].count for i in range(0, n_lps, max(1, n_lps // 4096)))
+        eng.fini()
+        return res
+
+    for _ in range(args.warmup):
+        one_step(False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    steps = [one_step(False) for _ in range(args.steps)]
+    e2e_steps = [one_step(True) for _ in range(max(1, min(args.steps, 2)))]
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    dev_s = sum(s["device_s"] for s in steps)
+    committed = sum(s["committed"] for s in steps)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s = float(t.item())
+        c = torch.tensor([committed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        committed = float(c.item())
+    value = committed / dev_s
+    e2e_value = sum(s["committed"] for s in e2e_steps) / sum(s["wall_s"] for s in e2e_steps)
+    peak, peak_src = measured_peak()
+    achieved = B_ALG_PHOLD * value / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "models/phold (unmodified reference sources), %d LPs, --simulation-time %g, master seed %d, "
+                               "one step = one full run; inputs larger than L2 (LP table + calendar >> 126 MB)" % (n_lps, T, MASTER_SEED),
+                   "lps": n_lps, "simulation_time": T, "committed_events_per_step": committed / args.steps,
+                   "windows_per_step": steps[0]["windows"], "rollbacks_per_step": steps[0]["rollbacks"],
+                   "executed_per_step": steps[0]["executed"], "silent_per_step": steps[0]["silent"]},
+        "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": 8 * n_lps + C.sizeof(rs_host.Config),
+                "d2h_bytes_per_step": 32 * n_lps + C.sizeof(rs_host.Stats)},
+        "gpu_launches": int(sum(s["launches"] for s in steps)),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel": "whole event loop (all engine kernels)",
+                     "algorithmic_bytes_per_event": B_ALG_PHOLD},
+        "clocks": sampler.summary(),
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(1)
+        print(json.dumps(line))
+
+
+def cpu_baseline(runs):
+    """The reference's own optimistic engine (--wt <host cores>) on a bounded sample of the workload:
+    1024 of the LPs, --simulation-time 150 (the reference cannot hold more than 250000 LPs and needs
+    4 MiB of stack per LP, SURVEY.md top)."""
+    exe = os.path.join(REPO, "oracle", "_ref", "phold")
+    cores = os.cpu_count() or 1
+    if os.path.exists(exe):
+        best = None
+        for _ in range(runs):
+            with tempfile.TemporaryDirectory() as td:
+                os.makedirs(os.path.join(td, ".rootsim"))
+                open(os.path.join(td, ".rootsim", "numerical.conf"), "w").write("%d\n" % MASTER_SEED)
+                env = dict(os.environ, HOME=td)
+                wt = max(1, min(cores, 32))
+                subprocess.run([exe, "--wt", str(wt), "--lp", "1024", "--simulation-time", "150", "--deterministic-seed",
+                                "--output-dir", os.path.join(td, "o")], env=env, cwd=td, capture_output=True, text=True, timeout=900)
+                txt = open(os.path.join(td, "o", "execution_stats")).read()
+                committed = float([l for l in txt.split("\n") if l.startswith("TOTAL COMMITTED EVENTS")][0].split(":")[1])
+                secs = float([l for l in txt.split("\n") if l.startswith("TOTAL SIMULATION TIME")][0].split(":")[1].split()[0])
+                v = committed / secs
+                best = v if best is None else max(best, v)
+        return {"value": best, "unit": "events/s", "cores": wt, "kind": "reference",
+                "sample": "unmodified ROOT-Sim 2.0.0 (oracle/_ref/phold) --wt %d --lp 1024 --simulation-time 150; the reference "
+                          "cannot run 1M LPs (MAX_LPs 250000, 4 MiB stack per LP)" % wt}
+    import rs_trace
+    _, _, out = rs_trace.run_oracle("phold", 65536, sim_time=60, horizon=60)
+    v = float(out.strip().split("events_per_s=")[1].split()[0])
+    return {"value": v, "unit": "events/s", "cores": 1, "kind": "port",
+            "sample": "oracle/seqsim.c (sequential restatement) phold --lp 65536 --simulation-time 60"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    for _ in range(args.warmup):
+        cpu_baseline(1)
+    vals = [cpu_baseline(1) for _ in range(args.steps)]
+    t1 = time.perf_counter()
+    v = sum(x["value"] for x in vals) / len(vals)
+    cb = dict(vals[0], value=v)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "events/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (t1 - t0) / max(1, args.steps + args.warmup),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "models/phold on the host CPU: " + cb["sample"]},
+        "cpu_baseline": cb, "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lps", type=int, default=1 << 20)
+    ap.add_argument("--sim-time", type=float, default=100.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -131,6 +131,10 @@ typedef struct rs_engine rs_engine_t;
  * src/core/init.c:385-390 (model_argp) and src/lib/topology/topology.c:210-214 (topology_settings). */
 void rs_model_info(rs_model_info_t *out);
 
+/* Hand model-specific command line options to the model's own argp parser (for callers that do not
+ * go through host/rs_main.c).  argv[0] is skipped, like main()'s.  Returns 0 on success. */
+int rs_model_args(int argc, char **argv);
+
 /* Fill cfg with the defaults of the reference CLI (src/core/init.c:315-340) and of the engine. */
 void rs_config_defaults(rs_config_t *cfg);
 

@@ -74,7 +74,7 @@ class ModelInfo(C.Structure):
                 ("topology_path", C.c_char_p), ("engine", C.c_char_p)]
 
 
-EXPORTS = ["rs_model_info", "rs_config_defaults", "rs_host_lp_seeds", "rs_dev_init", "rs_dev_run", "rs_dev_stats",
+EXPORTS = ["rs_model_args", "rs_model_info", "rs_config_defaults", "rs_host_lp_seeds", "rs_dev_init", "rs_dev_run", "rs_dev_stats",
            "rs_dev_trace", "rs_dev_lp_state", "rs_dev_exchange_info", "rs_dev_error", "rs_dev_fini"]
 
 
@@ -82,6 +82,8 @@ def load(path):
     lib = C.CDLL(path)
     lib.rs_model_info.argtypes = [C.POINTER(ModelInfo)]
     lib.rs_model_info.restype = None
+    lib.rs_model_args.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    lib.rs_model_args.restype = C.c_int
     lib.rs_config_defaults.argtypes = [C.POINTER(Config)]
     lib.rs_config_defaults.restype = None
     lib.rs_host_lp_seeds.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
@@ -106,7 +108,17 @@ def load(path):
 class Engine:
     """One device engine (one GPU, one block of LPs)."""
 
-    def __init__(self, lib_path):
+    def __init__(self, lib_path, private=False):
+        """private=True loads a private copy of the library, so that the model's file-scope option
+        variables (set through model_args) start from their defaults."""
+        self._tmp = None
+        if private:
+            import shutil
+            import tempfile
+            fd, self._tmp = tempfile.mkstemp(suffix=".so", prefix="rs_private_")
+            os.close(fd)
+            shutil.copy(lib_path, self._tmp)
+            lib_path = self._tmp
         self.lib = load(lib_path)
         self.h = C.c_void_p()
         self.cfg = Config()
@@ -116,6 +128,14 @@ class Engine:
         mi = ModelInfo()
         self.lib.rs_model_info(C.byref(mi))
         return mi
+
+    def model_args(self, args):
+        """Pass model-specific options (e.g. ["--tau", "3"]) to the model's argp parser."""
+        argv = [b"model"] + [a.encode() for a in args]
+        arr = (C.c_char_p * (len(argv) + 1))(*argv, None)
+        rc = self.lib.rs_model_args(len(argv), arr)
+        if rc != 0:
+            raise RsError(2, "model rejected its options %r" % (args,))
 
     def init(self, host_seeds=None, **kw):
         for k, v in kw.items():
@@ -164,6 +184,12 @@ class Engine:
         if self.h:
             self.lib.rs_dev_fini(self.h)
             self.h = C.c_void_p()
+        if self._tmp:
+            try:
+                os.unlink(self._tmp)
+            except OSError:
+                pass
+            self._tmp = None
 
     def __enter__(self):
         return self

@@ -1,0 +1,70 @@
+"""Engine LOGIC on the CPU: the same unity source that nvcc compiles for sm_100a is built with g++ in
+thread-emulation mode (rootsim-cc --emu; kernels become serial loops) and its committed trace is
+compared BIT-EXACTLY (timestamps included) with the CPU oracle built with the same portable log.
+This is a test harness for the window/rollback/cancellation logic in a container without a GPU; it is
+not a product path (the shipped library has no CPU execution path, see test_abi.py)."""
+import os
+
+import pytest
+
+import rs_host
+import rs_trace
+
+PHOLD_MASK = [0, 4, 5, 6, 7]
+
+
+def run_emu(model, n, T, wev, margs=(), state_bytes=8, seed=rs_trace.MASTER_SEED, **cfg):
+    lib = rs_host.build_model(model, emu=True)
+    with rs_host.Engine(lib, private=True) as eng:
+        eng.model_args(list(margs))
+        eng.init(n_lps=n, master_seed=seed, simulation_time=T, window_events=wev, **cfg)
+        assert eng.run()
+        st = eng.stats()
+        rows = rs_trace.engine_rows(eng, state_bytes)
+    return rows, st
+
+
+@pytest.mark.parametrize("n,T,wev", [(64, 100, 100000), (1024, 60, 4096), (257, 80, 50), (4096, 40, 100000), (1, 50, 100), (2, 50, 100), (3, 150, 100)])
+def test_phold_emu_vs_oracle(oracle_built, n, T, wev):
+    if not rs_host.model_sources("phold") or not os.path.exists(os.path.join(oracle_built, "seqp_phold")):
+        pytest.skip("phold sources live in the reference tree")
+    rows, st = run_emu("phold", n, T, wev, arena_bytes=128)
+    _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+    assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
+    assert st.committed_events == sum(r[0] for r in orows)
+    assert st.status & ~0x1 == 0
+
+
+@pytest.mark.parametrize("n,T,wev,margs", [
+    (48, 200, 100000, ["--order-sensitive"]),
+    (63, 300, 50, ["--order-sensitive", "--mean", "1.5"]),
+    (1000, 100, 100000, []),
+    (300, 150, 2000, ["--token-prob", "0.9"]),
+])
+def test_mixnet_emu_vs_oracle(oracle_built, n, T, wev, margs):
+    rows, st = run_emu("mixnet", n, T, wev, margs, state_bytes=32, seed=42, arena_bytes=1024, max_payload=16, bucket_width=0.25)
+    _, orows, _ = rs_trace.run_oracle("mixnet", n, sim_time=T, horizon=T, state_bytes=32, seed=42, extra=margs)
+    assert rs_trace.compare(rows, orows) == []
+    assert st.rollbacks > 0          # the cases are sized so that the optimistic machinery is exercised
+
+
+def test_window_size_does_not_change_the_committed_trace(oracle_built):
+    a, sa = run_emu("mixnet", 200, 120, 64, state_bytes=32, seed=7, arena_bytes=1024, max_payload=16)
+    b, sb = run_emu("mixnet", 200, 120, 1 << 20, state_bytes=32, seed=7, arena_bytes=1024, max_payload=16, bucket_width=1.0)
+    assert rs_trace.compare(a, b) == []
+    assert sa.windows != sb.windows
+
+
+def test_model_termination_by_ongvt(oracle_built):
+    """Without --simulation-time the run ends once every LP's OnGVT holds on committed state
+    (src/gvt/ccgs.c:107-179); the sequential reference stops at the first instant where all agree, the
+    optimistic engine at the first window boundary after it => at least as many events per LP."""
+    lib = rs_host.build_model("mixnet", emu=True)
+    with rs_host.Engine(lib, private=True) as eng:
+        eng.model_args(["--tick-limit", "30"])
+        eng.init(n_lps=20, master_seed=5, simulation_time=0.0, window_events=500, arena_bytes=1024, max_payload=16)
+        assert eng.run()
+        st = eng.stats()
+        states = eng.lp_state(4)
+    ticks = [int.from_bytes(states[4 * i:4 * i + 4], "little") for i in range(20)]
+    assert st.all_lps_agree == 1 and min(ticks) >= 30

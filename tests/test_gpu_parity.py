@@ -1,0 +1,120 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every run goes through the C-ABI of the
+product library (lib<model>.so, nvcc sm_100a) and is compared with the CPU oracle built with the same
+portable log => BIT-EXACT on every field, timestamps and the per-LP event hash included; against the
+real reference's golden digests (libm log) integers are bit-exact and timestamps within 64 ULP."""
+import os
+
+import pytest
+
+import rs_host
+import rs_trace
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+PHOLD_MASK = [0, 4, 5, 6, 7]
+
+
+def run_gpu(model, n, T, margs=(), state_bytes=8, seed=rs_trace.MASTER_SEED, **cfg):
+    lib = rs_host.build_model(model)
+    with rs_host.Engine(lib, private=True) as eng:
+        assert eng.info().engine == b"cuda-sm100a"
+        eng.model_args(list(margs))
+        eng.init(n_lps=n, master_seed=seed, simulation_time=T, **cfg)
+        assert eng.run()
+        st = eng.stats()
+        rows = rs_trace.engine_rows(eng, state_bytes)
+    return rows, st
+
+
+def need(model, oracle_built):
+    try:
+        rs_host.build_model(model)
+    except FileNotFoundError:
+        pytest.skip("no library for model %s" % model)
+    if not os.path.exists(os.path.join(oracle_built, "seqp_" + model)):
+        pytest.skip("no oracle for model %s" % model)
+
+
+@pytest.mark.parametrize("n,T,wev", [(64, 100, 100000), (1024, 60, 4096), (1024, 100, 1 << 20), (257, 80, 50),
+                                     (4096, 40, 100000), (1, 50, 100), (2, 50, 100), (65536, 25, 1 << 20)])
+def test_phold_vs_oracle(oracle_built, n, T, wev):
+    need("phold", oracle_built)
+    rows, st = run_gpu("phold", n, T, window_events=wev, arena_bytes=128)
+    _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+    assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
+    assert st.committed_events == sum(r[0] for r in orows)
+    assert st.kernel_launches > 0
+
+
+def test_phold_vs_reference_golden(oracle_built):
+    """Against the UNMODIFIED reference's --sequential digest (tests/golden, libm log)."""
+    need("phold", oracle_built)
+    for name, n, T in (("phold_lp1024_T50", 1024, 50), ("phold_lp100_T120", 100, 120)):
+        _, grows = rs_trace.parse_digest(os.path.join(GOLD, name + ".trace"))
+        rows, _ = run_gpu("phold", n, T, window_events=8192, arena_bytes=128)
+        assert rs_trace.compare(rows, grows, state_mask=PHOLD_MASK, ts_ulp=64, check_hash=False) == []
+
+
+def test_phold_1m_lps_vs_oracle(oracle_built):
+    """BASELINE config 2 size (1,048,576 LPs) on a short horizon the oracle finishes in seconds."""
+    need("phold", oracle_built)
+    n, T = 1 << 20, 12.0
+    rows, st = run_gpu("phold", n, T, window_events=1 << 20, arena_bytes=128, max_pending=16 << 20)
+    _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+    assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
+    assert st.committed_events == sum(r[0] for r in orows)
+
+
+@pytest.mark.parametrize("n,T,wev,margs", [
+    (48, 200, 100000, ["--order-sensitive"]),
+    (63, 300, 50, ["--order-sensitive", "--mean", "1.5"]),
+    (1000, 100, 100000, []),
+    (300, 150, 2000, ["--token-prob", "0.9"]),
+    (20000, 60, 1 << 18, []),
+])
+def test_mixnet_vs_oracle(oracle_built, n, T, wev, margs):
+    need("mixnet", oracle_built)
+    rows, st = run_gpu("mixnet", n, T, margs, state_bytes=32, seed=42, window_events=wev, arena_bytes=1024, max_payload=16, bucket_width=0.25)
+    _, orows, _ = rs_trace.run_oracle("mixnet", n, sim_time=T, horizon=T, state_bytes=32, seed=42, extra=margs)
+    assert rs_trace.compare(rows, orows) == []
+    assert st.rollbacks > 0
+
+
+def test_size_independent_properties_at_full_size(oracle_built):
+    """1M LPs, longer horizon than the oracle can check quickly: the committed trace must not depend on
+    how the run is cut into windows (a checksum of per-LP digests), committed == sum of per-LP counts,
+    every rolled back execution is accounted for."""
+    need("phold", oracle_built)
+    n, T = 1 << 20, 30.0
+    a, sa = run_gpu("phold", n, T, window_events=1 << 20, arena_bytes=128, max_pending=24 << 20)
+    b, sb = run_gpu("phold", n, T, window_events=1 << 18, bucket_width=0.125, arena_bytes=128, max_pending=24 << 20)
+    assert sa.windows != sb.windows
+    assert rs_trace.compare(a, b, state_mask=PHOLD_MASK) == []
+    for st, rows in ((sa, a), (sb, b)):
+        assert st.committed_events == sum(r[0] for r in rows)
+        assert st.executed_events + st.silent_events >= st.committed_events
+        assert st.status & ~0x1 == 0
+
+
+def test_model_termination_by_ongvt(oracle_built):
+    need("mixnet", oracle_built)
+    lib = rs_host.build_model("mixnet")
+    with rs_host.Engine(lib, private=True) as eng:
+        eng.model_args(["--tick-limit", "30"])
+        eng.init(n_lps=500, master_seed=5, simulation_time=0.0, window_events=5000, arena_bytes=1024, max_payload=16)
+        assert eng.run()
+        st = eng.stats()
+        states = eng.lp_state(4)
+    ticks = [int.from_bytes(states[4 * i:4 * i + 4], "little") for i in range(500)]
+    assert st.all_lps_agree == 1 and min(ticks) >= 30
+
+
+def test_fatal_model_error_is_reported(oracle_built):
+    """An event scheduled in the past aborts the run (src/communication/communication.c:285-289)."""
+    need("mixnet", oracle_built)
+    lib = rs_host.build_model("mixnet")
+    with rs_host.Engine(lib, private=True) as eng:
+        eng.model_args(["--mean", "-1"])        # Expent() with a negative mean: the reference aborts too
+        with pytest.raises(rs_host.RsError):
+            eng.init(n_lps=64, master_seed=5, simulation_time=50.0, arena_bytes=1024, max_payload=16)
+            eng.run()

@@ -1,0 +1,38 @@
+"""rs_math.h: the portable log must stay within 1 ULP of glibc's log (so that replacing libm changes
+timestamps by ULPs only) -- checked over a few million points by a small C driver."""
+import os
+import subprocess
+import tempfile
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SRC = r"""
+#include <stdio.h>
+#include <math.h>
+#include <rs_math.h>
+int main(void) {
+  unsigned long long s = 88172645463325252ULL, maxulp = 0;
+  for (long i = 0; i < 4000000; i++) {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    double u = ((s >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+    double x = (i & 1) ? u : u * 1e6 * ((i & 2) ? 1e-300 : 1.0);
+    if (x <= 0) continue;
+    long long a = (long long)rs_d2u(rs_log(x)), b = (long long)rs_d2u(log(x));
+    unsigned long long d = a > b ? a - b : b - a;
+    if (d > maxulp) maxulp = d;
+  }
+  printf("%llu %a %a\n", maxulp, rs_log(1.0), rs_log(2.718281828459045));
+  return 0;
+}
+"""
+
+
+def test_rs_log_within_one_ulp_of_libm():
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(SRC)
+        exe = os.path.join(td, "t")
+        subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-I", os.path.join(REPO, "root-sim_b200", "include"), c, "-o", exe, "-lm"], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) <= 1
+    assert out[1] == "0x0p+0"
