@@ -53,6 +53,7 @@ enum {
 
 /* engine flags */
 #define RS_F_TRACE		0x1u	/* keep the per-LP committed-trace digest (count/hash/last ts)   */
+#define RS_F_KTIME		0x2u	/* time every kernel launch with CUDA events (diagnostic runs)    */
 
 /*
  * Run configuration.  Mirrors the fields of the reference's `rootsim_config` that matter on this
@@ -166,6 +167,15 @@ int rs_dev_lp_state(rs_engine_t *e, void *out, uint32_t bytes_per_lp, uint32_t n
 /* Multi-GPU plumbing (one engine per GPU; see DESIGN.md "multi-GPU"): buffers are device pointers
  * owned by the engine, exchanged by the caller (NCCL) between the phases of a window. */
 int rs_dev_exchange_info(rs_engine_t *e, void **outbox, uint64_t **outbox_counts, void **inbox, uint32_t *record_bytes, uint64_t *capacity);
+
+/* Per-kernel device time (only with RS_F_KTIME): CUDA events recorded around every launch on the
+ * engine's stream.  Returns the number of entries written. */
+typedef struct rs_kernel_time {
+	char name[32];
+	double total_ms;
+	uint64_t launches;
+} rs_kernel_time_t;
+int rs_dev_kernel_times(rs_engine_t *e, rs_kernel_time_t *out, int max_entries);
 
 const char *rs_dev_error(rs_engine_t *e);
 int rs_dev_fini(rs_engine_t *e);

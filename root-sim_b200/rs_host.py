@@ -18,6 +18,7 @@ ROOTSIM_CC = os.path.join(HERE, "bin", "rootsim-cc")
 
 RS_ABI_VERSION = 1
 RS_F_TRACE = 0x1
+RS_F_KTIME = 0x2
 
 STATUS_BITS = {
     0x0001: "BAD_RECEIVER", 0x0002: "PAST_EVENT", 0x0004: "RESERVED_TYPE", 0x0008: "MODEL_EXIT",
@@ -60,12 +61,18 @@ class Stats(C.Structure):
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d["big_groups"] = self.reserved[0]
+        d["spill_rounds"] = self.reserved[1]
         d["status_names"] = [n for b, n in STATUS_BITS.items() if self.status & b]
         return d
 
 
 class LpTrace(C.Structure):
     _fields_ = [("count", C.c_uint64), ("hash", C.c_uint64), ("last_ts", C.c_double), ("seed", C.c_uint64)]
+
+
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("total_ms", C.c_double), ("launches", C.c_uint64)]
 
 
 class ModelInfo(C.Structure):
@@ -75,7 +82,7 @@ class ModelInfo(C.Structure):
 
 
 EXPORTS = ["rs_model_args", "rs_model_info", "rs_config_defaults", "rs_host_lp_seeds", "rs_dev_init", "rs_dev_run", "rs_dev_stats",
-           "rs_dev_trace", "rs_dev_lp_state", "rs_dev_exchange_info", "rs_dev_error", "rs_dev_fini"]
+           "rs_dev_trace", "rs_dev_lp_state", "rs_dev_exchange_info", "rs_dev_kernel_times", "rs_dev_error", "rs_dev_fini"]
 
 
 def load(path):
@@ -98,6 +105,8 @@ def load(path):
     lib.rs_dev_trace.restype = C.c_int
     lib.rs_dev_lp_state.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     lib.rs_dev_lp_state.restype = C.c_int
+    lib.rs_dev_kernel_times.argtypes = [C.c_void_p, C.POINTER(KernelTime), C.c_int]
+    lib.rs_dev_kernel_times.restype = C.c_int
     lib.rs_dev_error.argtypes = [C.c_void_p]
     lib.rs_dev_error.restype = C.c_char_p
     lib.rs_dev_fini.argtypes = [C.c_void_p]
@@ -179,6 +188,11 @@ class Engine:
         if rc != 0:
             raise RsError(rc, "lp_state")
         return bytes(buf)
+
+    def kernel_times(self):
+        arr = (KernelTime * 32)()
+        n = self.lib.rs_dev_kernel_times(self.h, arr, 32)
+        return {arr[i].name.decode(): (arr[i].total_ms, arr[i].launches) for i in range(n)}
 
     def fini(self):
         if self.h:

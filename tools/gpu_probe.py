@@ -1,0 +1,40 @@
+#!/usr/bin/env python3
+"""Diagnostic run of the device engine: stats + per-kernel CUDA-event times (RS_F_KTIME)."""
+import json
+import os
+import sys
+import time
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "root-sim_b200"))
+sys.path.insert(0, os.path.join(REPO, "tests"))
+sys.path.insert(0, REPO)
+import bench  # noqa: E402
+import rs_host  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1])
+    T = float(sys.argv[2])
+    ktime = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    over = dict(kv.split("=") for kv in sys.argv[4:])
+    cfg = bench.phold_cfg(n, T)
+    cfg["flags"] = rs_host.RS_F_KTIME if ktime else 0
+    for k, v in over.items():
+        cfg[k] = float(v) if k == "bucket_width" else int(v)
+    eng = rs_host.Engine(rs_host.build_model("phold"))
+    t0 = time.time()
+    eng.init(**cfg)
+    t1 = time.time()
+    fin = eng.run()
+    t2 = time.time()
+    st = eng.stats().as_dict()
+    kt = eng.kernel_times()
+    eng.fini()
+    ev = st["committed_events"] - n
+    print(json.dumps({"lps": n, "T": T, "init_s": t1 - t0, "run_s": t2 - t1, "events_per_s_device": ev / st["device_seconds"],
+                      "stats": st, "kernel_ms": {k: [round(v[0], 3), v[1]] for k, v in sorted(kt.items(), key=lambda x: -x[1][0])}}))
+
+
+if __name__ == "__main__":
+    main()
