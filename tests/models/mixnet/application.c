@@ -55,28 +55,39 @@ void ProcessEvent(unsigned int me, simtime_t now, int event_type, token_t *conte
 {
 	token_t tok;
 	double u;
+	simtime_t when;
+	unsigned to;
 	(void)size;
+	/* NB: every RNG draw is sequenced through a local variable.  Drawing inside an argument list
+	 * (f(FindReceiver(), now + Expent(x))) has unspecified evaluation order in C: gcc and nvcc
+	 * order the two draws differently, and the trace would depend on the compiler. */
 
 	switch (event_type) {
 	case INIT:
 		s = malloc(sizeof(lp_state_t));
 		memset(s, 0, sizeof(lp_state_t));
 		SetState(s);
-		ScheduleNewEvent(me, 10 * Random(), TICK, NULL, 0);
+		when = 10 * Random();
+		ScheduleNewEvent(me, when, TICK, NULL, 0);
 		break;
 
 	case TICK:
 		s->ticks++;
-		ScheduleNewEvent(me, now + Expent(mean_delay), TICK, NULL, 0);
+		when = now + Expent(mean_delay);
+		ScheduleNewEvent(me, when, TICK, NULL, 0);
 		u = Random();
 		if (u < token_prob) {
 			tok.value = (unsigned)(1000000 * Random());
 			tok.hops = 0;
 			tok.born = now;
-			ScheduleNewEvent(FindReceiver(), now + Expent(mean_delay / 2), TOKEN, &tok, sizeof(tok));
+			to = FindReceiver();
+			when = now + Expent(mean_delay / 2);
+			ScheduleNewEvent(to, when, TOKEN, &tok, sizeof(tok));
 		}
-		if (u > 0.9)
-			ScheduleNewEvent(FindReceiver(), now, ZERO, NULL, 0);
+		if (u > 0.9) {
+			to = FindReceiver();
+			ScheduleNewEvent(to, now, ZERO, NULL, 0);
+		}
 		push_node(s, s->ticks);
 		if (s->n_nodes > 8)
 			pop_node(s);
@@ -93,7 +104,9 @@ void ProcessEvent(unsigned int me, simtime_t now, int event_type, token_t *conte
 			tok.value = order_sensitive ? content->value + 1 : (unsigned)(1000000 * Random());
 			tok.hops = content->hops + 1;
 			tok.born = content->born;
-			ScheduleNewEvent(FindReceiver(), now + Expent(mean_delay / 4), TOKEN, &tok, sizeof(tok));
+			to = FindReceiver();
+			when = now + Expent(mean_delay / 4);
+			ScheduleNewEvent(to, when, TOKEN, &tok, sizeof(tok));
 		}
 		break;
 
