@@ -48,6 +48,20 @@ def test_mixnet_emu_vs_oracle(oracle_built, n, T, wev, margs):
     assert st.rollbacks > 0          # the cases are sized so that the optimistic machinery is exercised
 
 
+def test_hot_lp_path(oracle_built):
+    """Twin LPs (same seed every 64 gids, src/lib/numerical.c:399-409) fire together and create LPs with
+    hundreds of events per window: exercises the deferred hot-LP phase, the cooperative sort of large
+    groups, the spill heap for in-window self events and long in-window arrival lists."""
+    if not rs_host.model_sources("phold") or not os.path.exists(os.path.join(oracle_built, "seqp_phold")):
+        pytest.skip("phold sources live in the reference tree")
+    n, T = 16384, 30
+    rows, st = run_emu("phold", n, T, 1 << 20, arena_bytes=128, hot_threshold=40)
+    _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+    assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
+    d = st.as_dict()
+    assert d["big_groups"] > 0 and d["spill_rounds"] > 0
+
+
 def test_window_size_does_not_change_the_committed_trace(oracle_built):
     a, sa = run_emu("mixnet", 200, 120, 64, state_bytes=32, seed=7, arena_bytes=1024, max_payload=16)
     b, sb = run_emu("mixnet", 200, 120, 1 << 20, state_bytes=32, seed=7, arena_bytes=1024, max_payload=16, bucket_width=1.0)
