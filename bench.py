@@ -79,11 +79,14 @@ def phold_cfg(n_lps, sim_time):
     """Pool sizing for shipped PHOLD (population grows ~ N*0.9*e^{0.04 t})."""
     import math
     pending = int(n_lps * (1.0 * math.exp(0.04 * sim_time) + 1.0) * 1.25) + (1 << 20)
-    rate = n_lps * 0.2 * math.exp(0.04 * sim_time)           # events per unit of simulated time at the end
+    # Per-LP seeds repeat every 64 gids (src/lib/numerical.c:399-409), so n_lps/64 "twin" LPs fire together
+    # and create hot LPs that receive about n_lps/64 times the average load.  Size the calendar bucket so
+    # that the hottest LP sees about a thousand events per bucket at the end of the run.
+    hot_rate = (n_lps / 64.0) * 0.2 * math.exp(0.04 * sim_time)
     bw = 0.0625
-    while rate * bw > 1.5e6 and bw > 1.0 / 1024:
+    while hot_rate * bw > 1024 and bw > 1.0 / 1024:
         bw /= 2
-    return dict(n_lps=n_lps, master_seed=MASTER_SEED, simulation_time=float(sim_time), window_events=1 << 21,
+    return dict(n_lps=n_lps, master_seed=MASTER_SEED, simulation_time=float(sim_time), window_events=1 << 20,
                 arena_bytes=128, max_pending=pending, bucket_width=bw, n_buckets=max(4096, int(160 / bw)),
                 gvt_snapshot_cycles=1 << 30, flags=0)
 

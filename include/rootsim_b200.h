@@ -81,8 +81,9 @@ typedef struct rs_config {
 	int32_t device;			/* CUDA device ordinal                                             */
 	uint32_t topology_geometry;	/* filled from the model's topology_settings by rs_model_info()    */
 	uint32_t topology_out_of;	/*   .out_of_topology                                              */
-	uint32_t hot_threshold;		/* LPs with more events than this in one window run last (0 = 256)  */
-	uint32_t reserved[5];
+	uint32_t hot_threshold;		/* LPs with more events than this in one window run last (0 = off)  */
+	uint32_t chain_target;		/* optimism control: wanted largest per-LP group per window (0=1024) */
+	uint32_t reserved[4];
 } rs_config_t;
 
 /* Aggregate counters; definitions follow src/statistics/statistics.h:87-103 and :345-349. */

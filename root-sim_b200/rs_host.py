@@ -44,7 +44,7 @@ class Config(C.Structure):
         ("arena_bytes", C.c_uint32), ("max_payload", C.c_uint32), ("flags", C.c_uint32),
         ("max_pending", C.c_uint64), ("max_window", C.c_uint32), ("max_out", C.c_uint32),
         ("device", C.c_int32), ("topology_geometry", C.c_uint32), ("topology_out_of", C.c_uint32),
-        ("hot_threshold", C.c_uint32), ("reserved", C.c_uint32 * 5),
+        ("hot_threshold", C.c_uint32), ("chain_target", C.c_uint32), ("reserved", C.c_uint32 * 4),
     ]
 
 
