@@ -48,8 +48,10 @@ enum {
 #define RS_ST_LATE_FULL		0x0200u	/* too many in-window arrivals for one LP                       */
 #define RS_ST_PAYLOAD		0x0400u	/* event payload larger than max_payload                        */
 #define RS_ST_NO_EVENTS		0x0800u	/* pending set became empty before the horizon                  */
+#define RS_ST_XCHG_FULL		0x1000u	/* inter-rank exchange slot exhausted (raise xchg_cap)          */
 #define RS_ST_FATAL_MASK	(RS_ST_PAST_EVENT | RS_ST_RESERVED_TYPE | RS_ST_MODEL_EXIT | RS_ST_ARENA_FULL | \
-				 RS_ST_POOL_FULL | RS_ST_WINDOW_FULL | RS_ST_OUT_FULL | RS_ST_HORIZON | RS_ST_LATE_FULL | RS_ST_PAYLOAD)
+				 RS_ST_POOL_FULL | RS_ST_WINDOW_FULL | RS_ST_OUT_FULL | RS_ST_HORIZON | RS_ST_LATE_FULL | RS_ST_PAYLOAD | \
+				 RS_ST_XCHG_FULL)
 
 /* engine flags */
 #define RS_F_TRACE		0x1u	/* keep the per-LP committed-trace digest (count/hash/last ts)   */
@@ -83,7 +85,10 @@ typedef struct rs_config {
 	uint32_t topology_out_of;	/*   .out_of_topology                                              */
 	uint32_t hot_threshold;		/* LPs with more events than this in one window run last (0 = off)  */
 	uint32_t chain_target;		/* optimism control: wanted largest per-LP group per window (0=1024) */
-	uint32_t reserved[4];
+	uint32_t rank;			/* this engine's rank and the number of ranks (one engine per GPU);  */
+	uint32_t nranks;		/*   nranks <= 1 means a single engine owning every LP              */
+	uint32_t xchg_cap;		/* records per peer and exchange step (0 = 65536)                   */
+	uint32_t reserved[1];
 } rs_config_t;
 
 /* Aggregate counters; definitions follow src/statistics/statistics.h:87-103 and :345-349. */
@@ -166,9 +171,30 @@ int rs_dev_stats(rs_engine_t *e, rs_stats_t *out);
 int rs_dev_trace(rs_engine_t *e, rs_lp_trace_t *out, uint32_t n);
 int rs_dev_lp_state(rs_engine_t *e, void *out, uint32_t bytes_per_lp, uint32_t n);
 
-/* Multi-GPU plumbing (one engine per GPU; see DESIGN.md "multi-GPU"): buffers are device pointers
- * owned by the engine, exchanged by the caller (NCCL) between the phases of a window. */
-int rs_dev_exchange_info(rs_engine_t *e, void **outbox, uint64_t **outbox_counts, void **inbox, uint32_t *record_bytes, uint64_t *capacity);
+/*
+ * Multi-GPU (one engine per GPU, LPs block-partitioned like src/core/core.c:275-300).  Every rank runs
+ * rs_dev_run in lock step; per window the ranks agree on the window (two small all-reduces: GVT as a
+ * MIN, bucket counts as a SUM -- the role of the MPI_Iallreduce(MIN) of src/communication/gvt.c:515-521)
+ * and exchange, once per straggler round, the events/antimessages that land inside the window and,
+ * once per window, the future events (role of the per-event MPI_Isend of src/communication/mpi.c:169-184).
+ * The engine does not pick a transport: it calls the two collectives below on buffers in ENGINE
+ * memory (device memory for the CUDA library).  rs_dev_comm_init_nccl installs an NCCL implementation
+ * (ncclAllReduce + grouped ncclSend/ncclRecv on the engine's stream, NVLink/NVSwitch inside one box).
+ */
+typedef struct rs_comm_ops {
+	void *ctx;
+	/* in-place all-reduce of n int64; op 0 = sum, 1 = max */
+	int (*allreduce_i64)(void *ctx, long long *buf, int n, int op, void *stream);
+	/* personalised exchange: slot p of send goes to rank p, slot q of recv comes from rank q */
+	int (*alltoall)(void *ctx, const void *send, void *recv, size_t bytes_per_peer, void *stream);
+} rs_comm_ops_t;
+int rs_dev_set_comm(rs_engine_t *e, const rs_comm_ops_t *ops);
+/* id128: 128-byte ncclUniqueId created by rank 0 with rs_nccl_unique_id and handed to all ranks by the
+ * launcher; libnccl_path NULL = "libnccl.so.2" (resolved with dlopen, no link-time dependency). */
+int rs_nccl_unique_id(void *id128, const char *libnccl_path);
+int rs_dev_comm_init_nccl(rs_engine_t *e, const void *id128, const char *libnccl_path);
+/* this rank's block of LPs under the reference's block distribution (src/core/core.c:275-300) */
+void rs_host_lp_block(uint32_t n_lps, uint32_t nranks, uint32_t rank, uint32_t *first, uint32_t *count);
 
 /* Per-kernel device time (only with RS_F_KTIME): CUDA events recorded around every launch on the
  * engine's stream.  Returns the number of entries written. */

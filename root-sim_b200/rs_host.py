@@ -23,7 +23,7 @@ RS_F_KTIME = 0x2
 STATUS_BITS = {
     0x0001: "BAD_RECEIVER", 0x0002: "PAST_EVENT", 0x0004: "RESERVED_TYPE", 0x0008: "MODEL_EXIT",
     0x0010: "ARENA_FULL", 0x0020: "POOL_FULL", 0x0040: "WINDOW_FULL", 0x0080: "OUT_FULL",
-    0x0100: "HORIZON", 0x0200: "LATE_FULL", 0x0400: "PAYLOAD", 0x0800: "NO_EVENTS",
+    0x0100: "HORIZON", 0x0200: "LATE_FULL", 0x0400: "PAYLOAD", 0x0800: "NO_EVENTS", 0x1000: "XCHG_FULL",
 }
 ERRORS = {0: "RS_OK", 1: "RS_ERR_NO_DEVICE", 2: "RS_ERR_BAD_CONFIG", 3: "RS_ERR_OOM", 4: "RS_ERR_CUDA",
           5: "RS_ERR_MODEL", 6: "RS_ERR_CAPACITY"}
@@ -44,7 +44,8 @@ class Config(C.Structure):
         ("arena_bytes", C.c_uint32), ("max_payload", C.c_uint32), ("flags", C.c_uint32),
         ("max_pending", C.c_uint64), ("max_window", C.c_uint32), ("max_out", C.c_uint32),
         ("device", C.c_int32), ("topology_geometry", C.c_uint32), ("topology_out_of", C.c_uint32),
-        ("hot_threshold", C.c_uint32), ("chain_target", C.c_uint32), ("reserved", C.c_uint32 * 4),
+        ("hot_threshold", C.c_uint32), ("chain_target", C.c_uint32), ("rank", C.c_uint32), ("nranks", C.c_uint32),
+        ("xchg_cap", C.c_uint32), ("reserved", C.c_uint32 * 1),
     ]
 
 
@@ -71,6 +72,14 @@ class LpTrace(C.Structure):
     _fields_ = [("count", C.c_uint64), ("hash", C.c_uint64), ("last_ts", C.c_double), ("seed", C.c_uint64)]
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p)
+ALLTOALL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+class CommOps(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("allreduce_i64", ALLREDUCE_FN), ("alltoall", ALLTOALL_FN)]
+
+
 class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("total_ms", C.c_double), ("launches", C.c_uint64)]
 
@@ -82,7 +91,8 @@ class ModelInfo(C.Structure):
 
 
 EXPORTS = ["rs_model_args", "rs_model_info", "rs_config_defaults", "rs_host_lp_seeds", "rs_dev_init", "rs_dev_run", "rs_dev_stats",
-           "rs_dev_trace", "rs_dev_lp_state", "rs_dev_exchange_info", "rs_dev_kernel_times", "rs_dev_error", "rs_dev_fini"]
+           "rs_dev_trace", "rs_dev_lp_state", "rs_dev_set_comm", "rs_nccl_unique_id", "rs_dev_comm_init_nccl", "rs_host_lp_block",
+           "rs_dev_kernel_times", "rs_dev_error", "rs_dev_fini"]
 
 
 def load(path):
@@ -105,6 +115,14 @@ def load(path):
     lib.rs_dev_trace.restype = C.c_int
     lib.rs_dev_lp_state.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     lib.rs_dev_lp_state.restype = C.c_int
+    lib.rs_dev_set_comm.argtypes = [C.c_void_p, C.POINTER(CommOps)]
+    lib.rs_dev_set_comm.restype = C.c_int
+    lib.rs_nccl_unique_id.argtypes = [C.c_void_p, C.c_char_p]
+    lib.rs_nccl_unique_id.restype = C.c_int
+    lib.rs_dev_comm_init_nccl.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+    lib.rs_dev_comm_init_nccl.restype = C.c_int
+    lib.rs_host_lp_block.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.rs_host_lp_block.restype = None
     lib.rs_dev_kernel_times.argtypes = [C.c_void_p, C.POINTER(KernelTime), C.c_int]
     lib.rs_dev_kernel_times.restype = C.c_int
     lib.rs_dev_error.argtypes = [C.c_void_p]
@@ -189,6 +207,18 @@ class Engine:
             raise RsError(rc, "lp_state")
         return bytes(buf)
 
+    def set_comm(self, ops):
+        """Install caller-provided collectives (tests: torch.distributed/gloo on host memory)."""
+        self._comm = ops        # keep the callbacks alive
+        rc = self.lib.rs_dev_set_comm(self.h, C.byref(ops))
+        if rc != 0:
+            raise RsError(rc, "set_comm")
+
+    def comm_init_nccl(self, id128, libpath=None):
+        rc = self.lib.rs_dev_comm_init_nccl(self.h, id128, libpath.encode() if libpath else None)
+        if rc != 0:
+            raise RsError(rc, self.lib.rs_dev_error(self.h).decode())
+
     def kernel_times(self):
         arr = (KernelTime * 32)()
         n = self.lib.rs_dev_kernel_times(self.h, arr, 32)
@@ -210,6 +240,12 @@ class Engine:
 
     def __exit__(self, *a):
         self.fini()
+
+
+def lp_block(lib, n_lps, nranks, rank):
+    first, count = C.c_uint32(), C.c_uint32()
+    lib.rs_host_lp_block(n_lps, nranks, rank, C.byref(first), C.byref(count))
+    return first.value, count.value
 
 
 def lp_seeds(lib, master_seed, lp_first, lp_count):

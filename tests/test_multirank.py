@@ -1,0 +1,68 @@
+"""Multi-rank path on the CPU: world_size 2 and 3 over torch.distributed/gloo, engine in emulation build.
+The LPs are block-partitioned like the reference (src/core/core.c:275-300); events that cross ranks are
+exchanged once per straggler round / once per window; every rank must take the same window decisions.
+The union of the per-rank committed traces must equal the single-engine oracle BIT-EXACTLY."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+import rs_host
+import rs_trace
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def run_ranks(world, spec, tmp_path):
+    spec = dict(spec, out=str(tmp_path / "out.json"))
+    port = free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "multirank_worker.py"), json.dumps(spec)],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+    got = json.load(open(spec["out"]))
+    rows = []
+    for g in sorted(got, key=lambda g: g["first"]):
+        rows += [(r[0], r[1], r[2], r[3], bytes.fromhex(r[4])) for r in g["rows"]]
+    return rows, got
+
+
+@pytest.mark.parametrize("world,n,T", [(2, 512, 60), (3, 1000, 40), (2, 4096, 30)])
+def test_phold_multirank_vs_oracle(oracle_built, tmp_path, world, n, T):
+    if not rs_host.model_sources("phold") or not os.path.exists(os.path.join(oracle_built, "seqp_phold")):
+        pytest.skip("phold sources live in the reference tree")
+    rs_host.build_model("phold", emu=True)
+    spec = {"model": "phold", "n": n, "state_bytes": 8,
+            "cfg": dict(master_seed=rs_trace.MASTER_SEED, simulation_time=float(T), window_events=4096, arena_bytes=128)}
+    rows, got = run_ranks(world, spec, tmp_path)
+    _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+    assert rs_trace.compare(rows, orows, state_mask=[0, 4, 5, 6, 7]) == []
+    assert sum(g["stats"]["committed_events"] for g in got) == sum(r[0] for r in orows)
+    assert len({g["stats"]["windows"] for g in got}) == 1          # lock step: same number of windows everywhere
+
+
+def test_mixnet_multirank_vs_oracle(oracle_built, tmp_path):
+    """payloads, zero-delay events across ranks (antimessages travel between ranks), model heap"""
+    rs_host.build_model("mixnet", emu=True)
+    n, T = 301, 120
+    spec = {"model": "mixnet", "n": n, "state_bytes": 32, "margs": ["--order-sensitive", "--mean", "2.0"],
+            "cfg": dict(master_seed=42, simulation_time=float(T), window_events=2048, arena_bytes=1024, max_payload=16, bucket_width=0.25)}
+    rows, got = run_ranks(3, spec, tmp_path)
+    _, orows, _ = rs_trace.run_oracle("mixnet", n, sim_time=T, horizon=T, state_bytes=32, seed=42, extra=spec["margs"])
+    assert rs_trace.compare(rows, orows) == []
+    assert sum(g["stats"]["antimessages"] for g in got) > 0
