@@ -100,32 +100,54 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path")
     torch.cuda.set_device(local)
+    import torch.distributed as dist
     if world > 1:
-        import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib_path = rs_host.build_model("phold")
     n_lps, T = args.lps, args.sim_time
     cfg = phold_cfg(n_lps, T)
     cfg["device"] = local
     lib = rs_host.load(lib_path)
-    seeds = rs_host.lp_seeds(lib, MASTER_SEED, 0, n_lps)
+    first, count = rs_host.lp_block(lib, n_lps, world, rank)
+    seeds = rs_host.lp_seeds(lib, MASTER_SEED, first, count)
+    if world > 1:
+        cfg.update(rank=rank, nranks=world, lp_first=first, lp_count=count)
+        # one NCCL communicator for the engines (id made by rank 0, broadcast by the launcher's process group)
+        idbuf = (C.c_ubyte * 128)()
+        if rank == 0:
+            assert lib.rs_nccl_unique_id(idbuf, None) == 0
+        t = torch.tensor(list(idbuf), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        idbuf = (C.c_ubyte * 128)(*t.cpu().tolist())
 
     def one_step(e2e):
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         eng = rs_host.Engine(lib_path)
         eng.init(host_seeds=seeds if e2e else None, **cfg)
+        if world > 1:
+            eng.comm_init_nccl(idbuf)
         fin = eng.run()
         st = eng.stats()
         tr = eng.trace() if e2e else None
         t1 = time.perf_counter()
         assert fin and (st.status & ~0x1) == 0, st.as_dict()
-        committed = st.committed_events - n_lps       # INIT events are processed at engine creation
+        committed = st.committed_events - count       # INIT events are processed at engine creation
         res = dict(committed=committed, device_s=st.device_seconds, wall_s=t1 - t0, launches=st.kernel_launches,
                    windows=st.windows, rollbacks=st.rollbacks, executed=st.executed_events, silent=st.silent_events,
                    rounds=st.relax_rounds, late=st.late_events, antimessages=st.antimessages)
         if e2e:
-            res["count_sum"] = sum(tr[i].count for i in range(0, n_lps, max(1, n_lps // 4096)))
+            res["count_sum"] = sum(tr[i].count for i in range(0, count, max(1, count // 4096)))
         eng.fini()
+        if world > 1:
+            v = torch.tensor([res["device_s"], res["wall_s"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            c = torch.tensor([float(committed), float(res["launches"])], dtype=torch.float64, device="cuda")
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            res["device_s"], res["wall_s"] = float(v[0]), float(v[1])
+            res["committed"], res["launches"] = float(c[0]), float(c[1])
         return res
 
     for _ in range(args.warmup):
@@ -142,11 +164,13 @@ def run_ours(args):
     kcfg = dict(cfg, flags=rs_host.RS_F_KTIME)
     eng = rs_host.Engine(lib_path)
     eng.init(**kcfg)
+    if world > 1:
+        eng.comm_init_nccl(idbuf)
     eng.run()
     kst = eng.stats()
     ktimes = eng.kernel_times()
     eng.fini()
-    k_committed = kst.committed_events - n_lps
+    k_committed = kst.committed_events - count
     dom = max((k for k in ktimes if k not in ("k_init", "k_init_pool")), key=lambda k: ktimes[k][0])
     dom_ms, dom_launches = ktimes[dom]
 
@@ -188,16 +212,8 @@ def run_ours(args):
                         "hbm_frac_whole_loop": B_ALG_PHOLD * v / 1e9 / measured_peak()[0]}
         sup = dict(best, workload="models/phold, %d LPs, T=%g, one DISTINCT seed per LP (host seed array): no twin LPs" % (n_lps, T))
 
-    dev_s = sum(s["device_s"] for s in steps)
-    committed = sum(s["committed"] for s in steps)
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s = float(t.item())
-        c = torch.tensor([committed], dtype=torch.float64, device="cuda")
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        committed = float(c.item())
+    dev_s = sum(s["device_s"] for s in steps)          # already the max over ranks per step
+    committed = sum(s["committed"] for s in steps)      # already summed over ranks
     value = committed / dev_s
     e2e_value = sum(s["committed"] for s in e2e_steps) / sum(s["wall_s"] for s in e2e_steps)
     peak, peak_src = measured_peak()
@@ -212,7 +228,8 @@ def run_ours(args):
                    "lps": n_lps, "simulation_time": T, "committed_events_per_step": committed / args.steps,
                    "windows_per_step": steps[0]["windows"], "rollbacks_per_step": steps[0]["rollbacks"],
                    "executed_per_step": steps[0]["executed"], "silent_per_step": steps[0]["silent"],
-                   "bucket_width": cfg["bucket_width"]},
+                   "bucket_width": cfg["bucket_width"],
+                   "partition": "LPs block-partitioned over %d GPU(s), one engine per GPU, NCCL exchange per window" % world},
         "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": 8 * n_lps + C.sizeof(rs_host.Config),
                 "d2h_bytes_per_step": 32 * n_lps + C.sizeof(rs_host.Stats)},
         "gpu_launches": int(sum(s["launches"] for s in steps)),
@@ -232,6 +249,9 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(1)
         print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def cpu_baseline(runs):
