@@ -193,6 +193,10 @@ int rs_dev_set_comm(rs_engine_t *e, const rs_comm_ops_t *ops);
  * launcher; libnccl_path NULL = "libnccl.so.2" (resolved with dlopen, no link-time dependency). */
 int rs_nccl_unique_id(void *id128, const char *libnccl_path);
 int rs_dev_comm_init_nccl(rs_engine_t *e, const void *id128, const char *libnccl_path);
+/* A communicator shared by successive engines of one process (creation is collective and slow). */
+int rs_nccl_comm_create(const void *id128, int rank, int nranks, const char *libnccl_path, void **comm_out);
+int rs_dev_set_nccl_comm(rs_engine_t *e, void *comm);
+int rs_nccl_comm_destroy(void *comm);
 /* this rank's block of LPs under the reference's block distribution (src/core/core.c:275-300) */
 void rs_host_lp_block(uint32_t n_lps, uint32_t nranks, uint32_t rank, uint32_t *first, uint32_t *count);
 

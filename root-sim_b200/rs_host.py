@@ -91,7 +91,8 @@ class ModelInfo(C.Structure):
 
 
 EXPORTS = ["rs_model_args", "rs_model_info", "rs_config_defaults", "rs_host_lp_seeds", "rs_dev_init", "rs_dev_run", "rs_dev_stats",
-           "rs_dev_trace", "rs_dev_lp_state", "rs_dev_set_comm", "rs_nccl_unique_id", "rs_dev_comm_init_nccl", "rs_host_lp_block",
+           "rs_dev_trace", "rs_dev_lp_state", "rs_dev_set_comm", "rs_nccl_unique_id", "rs_dev_comm_init_nccl", "rs_nccl_comm_create", "rs_dev_set_nccl_comm",
+           "rs_nccl_comm_destroy", "rs_host_lp_block",
            "rs_dev_kernel_times", "rs_dev_error", "rs_dev_fini"]
 
 
@@ -121,6 +122,12 @@ def load(path):
     lib.rs_nccl_unique_id.restype = C.c_int
     lib.rs_dev_comm_init_nccl.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
     lib.rs_dev_comm_init_nccl.restype = C.c_int
+    lib.rs_nccl_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.rs_nccl_comm_create.restype = C.c_int
+    lib.rs_dev_set_nccl_comm.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rs_dev_set_nccl_comm.restype = C.c_int
+    lib.rs_nccl_comm_destroy.argtypes = [C.c_void_p]
+    lib.rs_nccl_comm_destroy.restype = C.c_int
     lib.rs_host_lp_block.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.rs_host_lp_block.restype = None
     lib.rs_dev_kernel_times.argtypes = [C.c_void_p, C.POINTER(KernelTime), C.c_int]
@@ -218,6 +225,11 @@ class Engine:
         rc = self.lib.rs_dev_comm_init_nccl(self.h, id128, libpath.encode() if libpath else None)
         if rc != 0:
             raise RsError(rc, self.lib.rs_dev_error(self.h).decode())
+
+    def set_nccl_comm(self, comm):
+        rc = self.lib.rs_dev_set_nccl_comm(self.h, comm)
+        if rc != 0:
+            raise RsError(rc, "set_nccl_comm")
 
     def kernel_times(self):
         arr = (KernelTime * 32)()
