@@ -48,6 +48,18 @@ def test_mixnet_emu_vs_oracle(oracle_built, n, T, wev, margs):
     assert st.rollbacks > 0          # the cases are sized so that the optimistic machinery is exercised
 
 
+@pytest.mark.parametrize("n,T,wev", [(16, 600, 4096), (64, 300, 256), (256, 120, 100000)])
+def test_pcs_emu_vs_oracle(oracle_built, n, T, wev):
+    """models/pcs unchanged: 40-byte payloads, malloc/free inside events (channel lists), hexagonal
+    topology, zero-delay HANDOFF_RECV between neighbours.  First 56 state bytes = counters, lvt, ta."""
+    if not rs_host.model_sources("pcs") or not os.path.exists(os.path.join(oracle_built, "seqp_pcs")):
+        pytest.skip("pcs sources live in the reference tree")
+    rows, st = run_emu("pcs", n, T, wev, state_bytes=56, arena_bytes=32768, max_payload=48, bucket_width=0.25, n_buckets=4096)
+    _, orows, _ = rs_trace.run_oracle("pcs", n, sim_time=T, horizon=T, state_bytes=56)
+    assert rs_trace.compare(rows, orows) == []
+    assert st.rollbacks > 0 and st.antimessages > 0
+
+
 def test_hot_lp_path(oracle_built):
     """Twin LPs (same seed every 64 gids, src/lib/numerical.c:399-409) fire together and create LPs with
     hundreds of events per window: exercises the deferred hot-LP phase, the cooperative sort of large

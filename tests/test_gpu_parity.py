@@ -80,6 +80,20 @@ def test_mixnet_vs_oracle(oracle_built, n, T, wev, margs):
     assert st.rollbacks > 0
 
 
+@pytest.mark.parametrize("n,T", [(16, 600), (1024, 150), (65536, 12)])
+def test_pcs_vs_oracle(oracle_built, n, T):
+    """models/pcs (BASELINE config 3 is 65536 cells = 256 x 256 hexagons): unchanged sources, 40-byte payloads,
+    malloc/free in events, zero-delay hand-offs.  Compared: counts, event hash, timestamps, RNG seeds and the
+    first 56 bytes of the state (all counters, lvt, ta); the per-call power/fading doubles further down in
+    the heap go through pow(), for which the device uses CUDA's libm (not part of the trace)."""
+    need("pcs", oracle_built)
+    rows, st = run_gpu("pcs", n, T, state_bytes=56, window_events=1 << 18, arena_bytes=32768, max_payload=48,
+                       bucket_width=0.25, n_buckets=4096, max_pending=8 * n + (1 << 20))
+    _, orows, _ = rs_trace.run_oracle("pcs", n, sim_time=T, horizon=T, state_bytes=56)
+    assert rs_trace.compare(rows, orows) == []
+    assert st.committed_events == sum(r[0] for r in orows)
+
+
 def test_size_independent_properties_at_full_size(oracle_built):
     """1M LPs, longer horizon than the oracle can check quickly: the committed trace must not depend on
     how the run is cut into windows (a checksum of per-LP digests), committed == sum of per-LP counts,
