@@ -209,6 +209,9 @@ typedef struct rs_kernel_time {
 } rs_kernel_time_t;
 int rs_dev_kernel_times(rs_engine_t *e, rs_kernel_time_t *out, int max_entries);
 
+/* diagnostics on stderr: 1 = one line per straggler round that needed a host decision */
+void rs_set_debug(int level);
+
 const char *rs_dev_error(rs_engine_t *e);
 int rs_dev_fini(rs_engine_t *e);
 

@@ -93,7 +93,7 @@ class ModelInfo(C.Structure):
 EXPORTS = ["rs_model_args", "rs_model_info", "rs_config_defaults", "rs_host_lp_seeds", "rs_dev_init", "rs_dev_run", "rs_dev_stats",
            "rs_dev_trace", "rs_dev_lp_state", "rs_dev_set_comm", "rs_nccl_unique_id", "rs_dev_comm_init_nccl", "rs_nccl_comm_create", "rs_dev_set_nccl_comm",
            "rs_nccl_comm_destroy", "rs_host_lp_block",
-           "rs_dev_kernel_times", "rs_dev_error", "rs_dev_fini"]
+           "rs_dev_kernel_times", "rs_set_debug", "rs_dev_error", "rs_dev_fini"]
 
 
 def load(path):

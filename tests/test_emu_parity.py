@@ -60,6 +60,19 @@ def test_pcs_emu_vs_oracle(oracle_built, n, T, wev):
     assert st.rollbacks > 0 and st.antimessages > 0
 
 
+def test_pcs_mutual_zero_delay_cycle(oracle_built):
+    """Regression: at 256 x 256 cells, cell 33 and its neighbour 289 share a seed (gid % 64) and hand a call
+    off to EACH OTHER at the bit-identical timestamp 29.087...; with eager cancellation the two LPs roll each
+    other back forever.  The receiver-side lazy cancellation makes the identical re-sent copy a no-op."""
+    if not rs_host.model_sources("pcs") or not os.path.exists(os.path.join(oracle_built, "seqp_pcs")):
+        pytest.skip("pcs sources live in the reference tree")
+    n, T = 65536, 30
+    rows, st = run_emu("pcs", n, T, 1 << 20, state_bytes=56, arena_bytes=8192, max_payload=48, bucket_width=0.25, n_buckets=4096,
+                       max_pending=16 * n)
+    _, orows, _ = rs_trace.run_oracle("pcs", n, sim_time=T, horizon=T, state_bytes=56)
+    assert rs_trace.compare(rows, orows) == []
+
+
 def test_hot_lp_path(oracle_built):
     """Twin LPs (same seed every 64 gids, src/lib/numerical.c:399-409) fire together and create LPs with
     hundreds of events per window: exercises the deferred hot-LP phase, the cooperative sort of large

@@ -80,7 +80,7 @@ def test_mixnet_vs_oracle(oracle_built, n, T, wev, margs):
     assert st.rollbacks > 0
 
 
-@pytest.mark.parametrize("n,T", [(16, 600), (1024, 150), (65536, 12)])
+@pytest.mark.parametrize("n,T", [(16, 600), (1024, 150), (65536, 40)])
 def test_pcs_vs_oracle(oracle_built, n, T):
     """models/pcs (BASELINE config 3 is 65536 cells = 256 x 256 hexagons): unchanged sources, 40-byte payloads,
     malloc/free in events, zero-delay hand-offs.  Compared: counts, event hash, timestamps, RNG seeds and the
