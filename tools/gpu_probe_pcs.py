@@ -16,6 +16,8 @@ def main():
     n = int(sys.argv[1])
     T = float(sys.argv[2])
     eng = rs_host.Engine(rs_host.build_model("pcs"))
+    if os.environ.get("RS_DEBUG"):
+        eng.lib.rs_set_debug(int(os.environ["RS_DEBUG"]))
     t0 = time.time()
     eng.init(n_lps=n, master_seed=rs_trace.MASTER_SEED, simulation_time=T, window_events=1 << 20, arena_bytes=32768,
              max_payload=48, bucket_width=0.25, n_buckets=4096, max_pending=16 * n + (1 << 20), flags=rs_host.RS_F_KTIME,
