@@ -107,3 +107,16 @@ def test_model_termination_by_ongvt(oracle_built):
         states = eng.lp_state(4)
     ticks = [int.from_bytes(states[4 * i:4 * i + 4], "little") for i in range(20)]
     assert st.all_lps_agree == 1 and min(ticks) >= 30
+
+
+def test_pool_exhaustion_is_reported_not_fatal_to_the_process(oracle_built):
+    """Capacity errors surface as RS_ERR_CAPACITY with the status bit set (no memory corruption, no hang)."""
+    lib = rs_host.build_model("mixnet", emu=True)
+    with rs_host.Engine(lib, private=True) as eng:
+        eng.model_args(["--token-prob", "1.0", "--mean", "0.5"])
+        eng.init(n_lps=3000, master_seed=3, simulation_time=400.0, window_events=4096, arena_bytes=1024, max_payload=16,
+                 bucket_width=4.0, n_buckets=64, max_pending=512)
+        with pytest.raises(rs_host.RsError) as ei:
+            eng.run()
+        assert ei.value.code == 6
+        assert set(eng.stats().as_dict()["status_names"]) & {"POOL_FULL", "OUT_FULL", "WINDOW_FULL"}

@@ -20,7 +20,7 @@ def main():
         eng.lib.rs_set_debug(int(os.environ["RS_DEBUG"]))
     t0 = time.time()
     eng.init(n_lps=n, master_seed=rs_trace.MASTER_SEED, simulation_time=T, window_events=1 << 20, arena_bytes=32768,
-             max_payload=48, bucket_width=0.25, n_buckets=4096, max_pending=16 * n + (1 << 20), flags=rs_host.RS_F_KTIME,
+             max_payload=48, bucket_width=0.25, n_buckets=4096, max_pending=256 * n + (1 << 20), flags=rs_host.RS_F_KTIME,
              gvt_snapshot_cycles=1 << 30)
     t1 = time.time()
     eng.run()
