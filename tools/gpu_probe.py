@@ -23,8 +23,23 @@ def main():
     for k, v in over.items():
         cfg[k] = float(v) if k == "bucket_width" else int(v)
     eng = rs_host.Engine(rs_host.build_model("phold"))
+    seeds = None
+    if os.environ.get("RS_DISTINCT_SEEDS"):
+        import ctypes as C
+        import numpy as np
+        g = np.arange(n, dtype=np.uint64)
+        z = (g * np.uint64(0x9E3779B97F4A7C15) + np.uint64(bench.MASTER_SEED))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        lo = (z & np.uint64(0xFFFFFFFF)) % np.uint64(0x9068FFFE) + np.uint64(1)
+        hi = (z >> np.uint64(32)) % np.uint64(0x464FFFFE) + np.uint64(1)
+        dseeds = ((hi << np.uint64(32)) | lo).astype(np.uint64)
+        seeds = (C.c_uint64 * n).from_buffer(dseeds)
+        cfg["bucket_width"] = 0.0625
+        cfg["n_buckets"] = 4096
     t0 = time.time()
-    eng.init(**cfg)
+    eng.init(host_seeds=seeds, **cfg)
     t1 = time.time()
     fin = eng.run()
     t2 = time.time()
