@@ -64,6 +64,8 @@ class Stats(C.Structure):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
         d["big_groups"] = self.reserved[0]
         d["spill_rounds"] = self.reserved[1]
+        d["redo_big"] = self.reserved[2]
+        d["redo_big_events"] = self.reserved[3]
         d["status_names"] = [n for b, n in STATUS_BITS.items() if self.status & b]
         return d
 
