@@ -253,7 +253,7 @@ def run_ours(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(1)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -301,7 +301,7 @@ def run_reference(args):
     t1 = time.perf_counter()
     v = sum(x["value"] for x in vals) / len(vals)
     cb = dict(vals[0], value=v)
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "events/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (t1 - t0) / max(1, args.steps + args.warmup),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -309,7 +309,18 @@ def run_reference(args):
         "cpu_baseline": cb, "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else the process prints (the model's own printf
+    from INIT runs on the device and lands on fd 1) is diverted to stderr for the duration of the run."""
+    sys.stdout.flush()
+    os.write(REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+REAL_STDOUT = os.dup(1)
+
+
 def main():
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
