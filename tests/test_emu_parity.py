@@ -120,3 +120,74 @@ def test_pool_exhaustion_is_reported_not_fatal_to_the_process(oracle_built):
             eng.run()
         assert ei.value.code == 6
         assert set(eng.stats().as_dict()["status_names"]) & {"POOL_FULL", "OUT_FULL", "WINDOW_FULL"}
+
+
+# ---------------------------------------------------------------- error paths and degenerate inputs
+def run_edge(fault, n=16, T=30.0, build=None, **cfg):
+    lib = (build or (lambda: rs_host.build_model("edgecases", emu=True)))()
+    with rs_host.Engine(lib, private=True) as eng:
+        eng.model_args(["--fault", str(fault)])
+        eng.init(n_lps=n, master_seed=9, simulation_time=T, window_events=256, arena_bytes=512, **cfg)
+        try:
+            fin = eng.run()
+            err = None
+        except rs_host.RsError as ex:
+            fin, err = None, ex
+        return fin, err, eng.stats().as_dict(), rs_trace.engine_rows(eng, 8)
+
+
+EDGE = [
+    # fault, expected error code (None = completes), expected status flag
+    (0, None, None),                      # healthy run
+    (1, 5, "PAST_EVENT"),                 # src/communication/communication.c:285-289: fatal
+    (2, 5, "RESERVED_TYPE"),              # :291-294: fatal
+    (3, None, "BAD_RECEIVER"),            # :280-283: warning, event dropped, run goes on
+    (4, 5, "MODEL_EXIT"),                 # model called exit()
+    (5, 6, "ARENA_FULL"),                 # per-LP heap exhausted: malloc returns NULL, capacity error reported
+    (6, None, "NO_EVENTS"),               # nothing was ever scheduled: the run ends with an empty calendar
+    (7, None, None),                      # one active LP, fifteen that only ever saw INIT (ragged input)
+]
+
+
+@pytest.mark.parametrize("fault,code,flag", EDGE, ids=["ok", "past", "reserved-type", "bad-receiver", "exit", "arena", "no-events", "one-active"])
+def test_edge_cases_emu(oracle_built, fault, code, flag):
+    fin, err, st, rows = run_edge(fault)
+    if code is None:
+        assert err is None and fin
+    else:
+        assert err is not None and err.code == code
+    if flag:
+        assert flag in st["status_names"]
+    if fault in (0, 3, 7):
+        extra = ["--fault", str(fault)]
+        _, orows, _ = rs_trace.run_oracle("edgecases", 16, sim_time=30.0, horizon=30.0, seed=9, extra=extra)
+        assert rs_trace.compare(rows, orows) == []
+    if fault == 6:
+        assert st["committed_events"] == 16 and [r[0] for r in rows] == [1] * 16      # INIT only
+    if fault == 7:
+        assert [r[0] for r in rows][1:] == [1] * 15 and rows[0][0] > 10
+
+
+def test_cli_executable_emu(oracle_built, tmp_path):
+    """host/rs_main.c: ROOT-Sim command line (--lp, --simulation-time, --seed, model options chained through
+    argp like src/core/init.c:385-390), execution_stats with the reference's labels, trace dump."""
+    import subprocess
+    import sys
+    exe = tmp_path / "mixnet_cli"
+    srcs = rs_host.model_sources("mixnet")
+    subprocess.run([sys.executable, rs_host.ROOTSIM_CC, "--emu"] + srcs + ["-o", str(exe)], check=True, capture_output=True)
+    out = tmp_path / "out"
+    tr = tmp_path / "trace.txt"
+    r = subprocess.run([str(exe), "--lp", "200", "--simulation-time", "60", "--seed", "42", "--wt", "4", "--no-core-binding",
+                        "--b200-arena-bytes", "1024", "--b200-max-payload", "16", "--b200-bucket-width", "0.25",
+                        "--output-dir", str(out), "--b200-trace", str(tr), "--mean", "3.0"], capture_output=True, text=True)
+    assert r.returncode == 0 and "SIMULATION CORRECTLY COMPLETED" in r.stdout
+    stats = open(out / "execution_stats").read()
+    for label in ("TOTAL EXECUTED EVENTS", "TOTAL COMMITTED EVENTS", "TOTAL ROLLBACKS EXECUTED", "TOTAL ANTIMESSAGES", "EFFICIENCY", "LAST COMMITTED GVT"):
+        assert label in stats
+    _, rows = rs_trace.parse_digest(str(tr))
+    _, orows, _ = rs_trace.run_oracle("mixnet", 200, sim_time=60, horizon=60, seed=42, extra=["--mean", "3.0"])
+    assert rs_trace.compare(rows, orows) == []
+    # the sequential engine is the reference's own: asking this runtime for it is an error, like an unknown option
+    r = subprocess.run([str(exe), "--lp", "8", "--sequential"], capture_output=True, text=True)
+    assert r.returncode != 0

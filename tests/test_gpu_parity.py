@@ -132,3 +132,57 @@ def test_fatal_model_error_is_reported(oracle_built):
         with pytest.raises(rs_host.RsError):
             eng.init(n_lps=64, master_seed=5, simulation_time=50.0, arena_bytes=1024, max_payload=16)
             eng.run()
+
+
+EDGE = [
+    (0, None, None), (1, 5, "PAST_EVENT"), (2, 5, "RESERVED_TYPE"), (3, None, "BAD_RECEIVER"), (4, 5, "MODEL_EXIT"),
+    (5, 6, "ARENA_FULL"), (6, None, "NO_EVENTS"), (7, None, None),
+]
+
+
+@pytest.mark.parametrize("fault,code,flag", EDGE, ids=["ok", "past", "reserved-type", "bad-receiver", "exit", "arena", "no-events", "one-active"])
+def test_edge_cases(oracle_built, fault, code, flag):
+    """Error behaviour of the event API (src/communication/communication.c:280-294), model exit, heap
+    exhaustion, a model that schedules nothing, and fifteen LPs that only ever see INIT."""
+    need("edgecases", oracle_built)
+    lib = rs_host.build_model("edgecases")
+    with rs_host.Engine(lib, private=True) as eng:
+        eng.model_args(["--fault", str(fault)])
+        eng.init(n_lps=16, master_seed=9, simulation_time=30.0, window_events=256, arena_bytes=512)
+        err = None
+        try:
+            fin = eng.run()
+        except rs_host.RsError as ex:
+            fin, err = None, ex
+        st = eng.stats().as_dict()
+        rows = rs_trace.engine_rows(eng, 8)
+    if code is None:
+        assert err is None and fin
+    else:
+        assert err is not None and err.code == code
+    if flag:
+        assert flag in st["status_names"]
+    if fault in (0, 3, 7):
+        _, orows, _ = rs_trace.run_oracle("edgecases", 16, sim_time=30.0, horizon=30.0, seed=9, extra=["--fault", str(fault)])
+        assert rs_trace.compare(rows, orows) == []
+    if fault == 6:
+        assert [r[0] for r in rows] == [1] * 16
+
+
+def test_cli_executable(oracle_built, tmp_path):
+    """The ROOT-Sim style executable (host/rs_main.c + lib<model>.so, built by __graft_entry__.build())."""
+    import subprocess
+    need("mixnet", oracle_built)
+    exe = os.path.join(rs_host.BUILT, "mixnet")
+    if not os.path.exists(exe):
+        pytest.skip("executable not built")
+    out, tr = tmp_path / "out", tmp_path / "trace.txt"
+    r = subprocess.run([exe, "--lp", "2000", "--simulation-time", "60", "--seed", "42", "--wt", "4", "--b200-arena-bytes", "1024",
+                        "--b200-max-payload", "16", "--b200-bucket-width", "0.25", "--output-dir", str(out), "--b200-trace", str(tr),
+                        "--mean", "3.0"], capture_output=True, text=True)
+    assert r.returncode == 0 and "SIMULATION CORRECTLY COMPLETED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    stats = open(out / "execution_stats").read()
+    assert "TOTAL COMMITTED EVENTS" in stats and "EFFICIENCY" in stats
+    _, rows = rs_trace.parse_digest(str(tr))
+    _, orows, _ = rs_trace.run_oracle("mixnet", 2000, sim_time=60, horizon=60, seed=42, extra=["--mean", "3.0"])
+    assert rs_trace.compare(rows, orows) == []
