@@ -84,7 +84,7 @@ typedef struct rs_config {
 	uint32_t topology_geometry;	/* filled from the model's topology_settings by rs_model_info()    */
 	uint32_t topology_out_of;	/*   .out_of_topology                                              */
 	uint32_t hot_threshold;		/* LPs with more events than this in one window run last (0 = off)  */
-	uint32_t chain_target;		/* optimism control: wanted largest per-LP group per window (0=1024) */
+	uint32_t chain_target;		/* optimism control: wanted largest per-LP group per window (0=8192) */
 	uint32_t rank;			/* this engine's rank and the number of ranks (one engine per GPU);  */
 	uint32_t nranks;		/*   nranks <= 1 means a single engine owning every LP              */
 	uint32_t xchg_cap;		/* records per peer and exchange step (0 = 65536)                   */
