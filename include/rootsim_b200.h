@@ -88,7 +88,7 @@ typedef struct rs_config {
 	uint32_t rank;			/* this engine's rank and the number of ranks (one engine per GPU);  */
 	uint32_t nranks;		/*   nranks <= 1 means a single engine owning every LP              */
 	uint32_t xchg_cap;		/* records per peer and exchange step (0 = 65536)                   */
-	uint32_t reserved[1];
+	uint32_t chunk_events;		/* optional: an LP pauses after this many events per pass (0 = off)      */
 } rs_config_t;
 
 /* Aggregate counters; definitions follow src/statistics/statistics.h:87-103 and :345-349. */

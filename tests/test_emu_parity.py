@@ -191,3 +191,29 @@ def test_cli_executable_emu(oracle_built, tmp_path):
     # the sequential engine is the reference's own: asking this runtime for it is an error, like an unknown option
     r = subprocess.run([str(exe), "--lp", "8", "--sequential"], capture_output=True, text=True)
     assert r.returncode != 0
+
+
+# ---------------------------------------------------------------- checkpoint ring and chunked execution
+@pytest.mark.parametrize("chunk,period", [(1, 1), (2, 3), (5, 2), (3, 1000000)])
+def test_chunked_execution_and_checkpoint_ring(oracle_built, chunk, period):
+    """Tiny chunk_events / ckpt_period force every LP to pause after a few events and to take in-window
+    checkpoints constantly: resume-after-pause, rollback to a ring record, rollback of a paused LP, the
+    own-pending-events snapshot in the records, and annihilation of self-addressed events at rollback are
+    all exercised on three models; the committed trace must not change."""
+    cases = [("mixnet", 300, 150, ["--token-prob", "0.9"], 32, dict(seed=42),
+              dict(master_seed=42, window_events=2000, arena_bytes=1024, max_payload=16, bucket_width=0.25), None)]
+    if rs_host.model_sources("phold") and os.path.exists(os.path.join(oracle_built, "seqp_phold")):
+        cases.append(("phold", 1024, 60, [], 8, {}, dict(master_seed=rs_trace.MASTER_SEED, window_events=1 << 20, arena_bytes=128, chain_target=64), PHOLD_MASK))
+        cases.append(("pcs", 64, 300, [], 56, {}, dict(master_seed=rs_trace.MASTER_SEED, window_events=256, arena_bytes=32768, max_payload=48,
+                                                      bucket_width=0.25, n_buckets=4096), None))
+    for model, n, T, margs, sb, okw, cfg, mask in cases:
+        lib = rs_host.build_model(model, emu=True)
+        with rs_host.Engine(lib, private=True) as eng:
+            eng.model_args(margs)
+            eng.init(n_lps=n, simulation_time=float(T), chunk_events=chunk, ckpt_period=period, **cfg)
+            assert eng.run()
+            st = eng.stats()
+            rows = rs_trace.engine_rows(eng, sb)
+        _, orows, _ = rs_trace.run_oracle(model, n, sim_time=T, horizon=T, state_bytes=sb, extra=margs, **okw)
+        assert rs_trace.compare(rows, orows, state_mask=mask) == [], (model, chunk, period)
+        assert st.rollbacks > 0
