@@ -23,6 +23,8 @@ def main():
     for k, v in over.items():
         cfg[k] = float(v) if k == "bucket_width" else int(v)
     eng = rs_host.Engine(rs_host.build_model("phold"))
+    if os.environ.get("RS_DEBUG"):
+        eng.lib.rs_set_debug(int(os.environ["RS_DEBUG"]))
     seeds = None
     if os.environ.get("RS_DISTINCT_SEEDS"):
         import ctypes as C
