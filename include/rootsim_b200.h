@@ -209,6 +209,12 @@ typedef struct rs_kernel_time {
 } rs_kernel_time_t;
 int rs_dev_kernel_times(rs_engine_t *e, rs_kernel_time_t *out, int max_entries);
 
+/* Diagnostic: the serial latency of the model's event handler on ONE device thread -- `iters` calls of
+ * ProcessEvent(lp, now+k*1e-3, type, NULL, 0, state) back to back (silent != 0: as in a coast-forward, sends
+ * suppressed).  This is what bounds a window whose longest per-LP chain dominates.  DESTRUCTIVE: the LP's state
+ * advances; use a scratch engine.  ns_per_event receives the mean. */
+int rs_dev_probe_event(rs_engine_t *e, uint32_t lp, int event_type, uint32_t iters, int silent, double *ns_per_event);
+
 /* diagnostics on stderr: 1 = one line per straggler round that needed a host decision */
 void rs_set_debug(int level);
 

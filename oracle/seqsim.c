@@ -573,6 +573,7 @@ int main(int argc, char **argv)
 		seq_schedule(g, 0.0, INIT, NULL, 0);
 	}
 
+	const long dbg_lp = getenv("RS_TRACE_LP") ? atol(getenv("RS_TRACE_LP")) : -1;
 	bool *done = calloc(n_prc_tot, sizeof(bool));
 	unsigned completed = 0;
 	uint64_t executed = 0;
@@ -586,6 +587,8 @@ int main(int argc, char **argv)
 		cur->lvt = e->ts;
 		ProcessEvent_light(cur_id, e->ts, e->type, e->size ? e->payload : NULL, e->size, cur->state);
 		executed++;
+		if (dbg_lp == (long)cur_id && e->ts < horizon)	/* RS_TRACE_LP: list one LP's events (debugging aid) */
+			fprintf(stderr, "[or lp %u] ts=%.17g\n", cur_id, e->ts);
 		if (e->ts < horizon) {
 			int32_t ty = e->type;
 			cur->t_count++; total_traced++;

@@ -87,6 +87,20 @@ def test_hot_lp_path(oracle_built):
     assert d["big_groups"] > 0 and d["spill_rounds"] > 0
 
 
+def test_own_event_queue_overflow_is_replayed_identically(oracle_built):
+    """A burst of in-window ARRIVALS (4096 twin senders, small group) overflows the LP's queue of own
+    in-window events, so some of them travel through the output buffer; a rollback into that stretch
+    restores a checkpoint record and replays silently -- the replay has to route every own event exactly
+    as the first execution did (regression: a larger queue after the restore executed one event twice)."""
+    if not rs_host.model_sources("phold") or not os.path.exists(os.path.join(oracle_built, "seqp_phold")):
+        pytest.skip("phold sources live in the reference tree")
+    n, T = 262144, 16
+    rows, st = run_emu("phold", n, T, 1 << 20, arena_bytes=128, max_pending=4 << 20)
+    _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+    assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
+    assert st.rollbacks > 0 and st.as_dict()["spill_rounds"] > 0
+
+
 def test_window_size_does_not_change_the_committed_trace(oracle_built):
     a, sa = run_emu("mixnet", 200, 120, 64, state_bytes=32, seed=7, arena_bytes=1024, max_payload=16)
     b, sb = run_emu("mixnet", 200, 120, 1 << 20, state_bytes=32, seed=7, arena_bytes=1024, max_payload=16, bucket_width=1.0)

@@ -36,7 +36,8 @@ def need(model, oracle_built):
 
 
 @pytest.mark.parametrize("n,T,wev", [(64, 100, 100000), (1024, 60, 4096), (1024, 100, 1 << 20), (257, 80, 50),
-                                     (4096, 40, 100000), (1, 50, 100), (2, 50, 100), (65536, 25, 1 << 20)])
+                                     (4096, 40, 100000), (1, 50, 100), (2, 50, 100), (65536, 25, 1 << 20),
+                                     (262144, 40, 1 << 20)])
 def test_phold_vs_oracle(oracle_built, n, T, wev):
     need("phold", oracle_built)
     rows, st = run_gpu("phold", n, T, window_events=wev, arena_bytes=128)

@@ -47,10 +47,16 @@ def main():
     t2 = time.time()
     st = eng.stats().as_dict()
     kt = eng.kernel_times()
+    hot = None
+    if os.environ.get("RS_HOTSTATS"):
+        import numpy as np
+        tr = eng.trace()
+        cnt = np.sort(np.frombuffer(tr, dtype=[("count", "u8"), ("hash", "u8"), ("last_ts", "f8"), ("seed", "u8")])["count"].astype(np.int64))[::-1]
+        hot = {"top": [int(x) for x in cnt[:8]], "over_1e4": int((cnt > 10000).sum()), "over_1e5": int((cnt > 100000).sum())}
     eng.fini()
     ev = st["committed_events"] - n
     print(json.dumps({"lps": n, "T": T, "init_s": t1 - t0, "run_s": t2 - t1, "events_per_s_device": ev / st["device_seconds"],
-                      "stats": st, "kernel_ms": {k: [round(v[0], 3), v[1]] for k, v in sorted(kt.items(), key=lambda x: -x[1][0])}}))
+                      "stats": st, "hot": hot, "kernel_ms": {k: [round(v[0], 3), v[1]] for k, v in sorted(kt.items(), key=lambda x: -x[1][0])}}))
 
 
 if __name__ == "__main__":
