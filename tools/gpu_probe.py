@@ -40,6 +40,13 @@ def main():
         seeds = (C.c_uint64 * n).from_buffer(dseeds)
         cfg["bucket_width"] = 0.0625
         cfg["n_buckets"] = 4096
+    if os.environ.get("RS_SAME_SEEDS"):
+        # every LP is a twin of every other: pure same-timestamp bursts on single LPs (profiling aid)
+        import ctypes as C
+        import numpy as np
+        one = rs_host.lp_seeds(eng.lib, bench.MASTER_SEED, 0, 1)[0]
+        dseeds = np.full(n, one, dtype=np.uint64)
+        seeds = (C.c_uint64 * n).from_buffer(dseeds)
     t0 = time.time()
     eng.init(host_seeds=seeds, **cfg)
     t1 = time.time()
