@@ -197,6 +197,15 @@ int rs_dev_comm_init_nccl(rs_engine_t *e, const void *id128, const char *libnccl
 int rs_nccl_comm_create(const void *id128, int rank, int nranks, const char *libnccl_path, void **comm_out);
 int rs_dev_set_nccl_comm(rs_engine_t *e, void *comm);
 int rs_nccl_comm_destroy(void *comm);
+/* Direct exchange over NVLink / NVSwitch peer memory (ranks = processes on ONE box): after rs_dev_init and
+ * the communicator, every rank exports a 64-byte handle of its inbox, the launcher gathers the nranks
+ * handles (rank order) and hands the array to every rank.  From then on an exchange step is one kernel that
+ * stores this rank's records straight into the peers' inboxes plus a one-word all-reduce as the barrier,
+ * instead of the fixed-size personalised exchange of rs_comm_ops_t.alltoall (which remains the path for
+ * other transports).  Engines of all ranks must be destroyed together (rs_dev_fini synchronises them). */
+#define RS_IPC_HANDLE_BYTES 64
+int rs_dev_ipc_export(rs_engine_t *e, void *handle64);
+int rs_dev_ipc_import(rs_engine_t *e, const void *handles /* nranks * RS_IPC_HANDLE_BYTES */);
 /* this rank's block of LPs under the reference's block distribution (src/core/core.c:275-300) */
 void rs_host_lp_block(uint32_t n_lps, uint32_t nranks, uint32_t rank, uint32_t *first, uint32_t *count);
 

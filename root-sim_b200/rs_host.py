@@ -95,7 +95,7 @@ class ModelInfo(C.Structure):
 EXPORTS = ["rs_model_args", "rs_model_info", "rs_config_defaults", "rs_host_lp_seeds", "rs_dev_init", "rs_dev_run", "rs_dev_stats",
            "rs_dev_trace", "rs_dev_lp_state", "rs_dev_set_comm", "rs_nccl_unique_id", "rs_dev_comm_init_nccl", "rs_nccl_comm_create", "rs_dev_set_nccl_comm",
            "rs_nccl_comm_destroy", "rs_host_lp_block",
-           "rs_dev_kernel_times", "rs_dev_probe_event", "rs_set_debug", "rs_dev_error", "rs_dev_fini"]
+           "rs_dev_kernel_times", "rs_dev_probe_event", "rs_dev_ipc_export", "rs_dev_ipc_import", "rs_set_debug", "rs_dev_error", "rs_dev_fini"]
 
 
 def load(path):
@@ -134,6 +134,10 @@ def load(path):
     lib.rs_host_lp_block.restype = None
     lib.rs_dev_kernel_times.argtypes = [C.c_void_p, C.POINTER(KernelTime), C.c_int]
     lib.rs_dev_kernel_times.restype = C.c_int
+    lib.rs_dev_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rs_dev_ipc_export.restype = C.c_int
+    lib.rs_dev_ipc_import.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rs_dev_ipc_import.restype = C.c_int
     lib.rs_dev_probe_event.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_double)]
     lib.rs_dev_probe_event.restype = C.c_int
     lib.rs_dev_error.argtypes = [C.c_void_p]
@@ -234,6 +238,22 @@ class Engine:
         rc = self.lib.rs_dev_set_nccl_comm(self.h, comm)
         if rc != 0:
             raise RsError(rc, "set_nccl_comm")
+
+    def ipc_export(self):
+        """64-byte handle of this rank's inbox (direct NVLink exchange)"""
+        buf = (C.c_ubyte * 64)()
+        rc = self.lib.rs_dev_ipc_export(self.h, buf)
+        if rc != 0:
+            raise RsError(rc, self.lib.rs_dev_error(self.h).decode())
+        return bytes(buf)
+
+    def ipc_import(self, handles):
+        """handles: the nranks exported handles in rank order"""
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        rc = self.lib.rs_dev_ipc_import(self.h, buf)
+        if rc != 0:
+            raise RsError(rc, self.lib.rs_dev_error(self.h).decode())
 
     def probe_event(self, lp, event_type, iters=10000, silent=False):
         """ns per handler call on one device thread (destructive diagnostic)"""

@@ -22,7 +22,7 @@ def main():
     cfg["flags"] = rs_host.RS_F_KTIME if ktime else 0
     for k, v in over.items():
         cfg[k] = float(v) if k == "bucket_width" else int(v)
-    eng = rs_host.Engine(rs_host.build_model("phold"))
+    eng = rs_host.Engine(os.environ.get("RS_LIB") or rs_host.build_model("phold"))
     if os.environ.get("RS_DEBUG"):
         eng.lib.rs_set_debug(int(os.environ["RS_DEBUG"]))
     seeds = None

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(REPO, "root-sim_b200"))
 import rs_host
 model = sys.argv[1] if len(sys.argv) > 1 else "phold"
 etype = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-lib = rs_host.lib_path(model)
+lib = os.environ.get("RS_LIB") or rs_host.lib_path(model)
 out = {}
 with rs_host.Engine(lib, private=True) as eng:
     eng.init(n_lps=1024, master_seed=1, simulation_time=10.0, max_out=1 << 20)

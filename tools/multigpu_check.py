@@ -35,6 +35,11 @@ def main():
     eng.init(n_lps=n, master_seed=rs_trace.MASTER_SEED, simulation_time=T, window_events=1 << 20, arena_bytes=128,
              device=local, rank=rank, nranks=world, lp_first=first, lp_count=count, max_pending=(n * 8 + (1 << 20)))
     eng.comm_init_nccl(idbuf)
+    if not os.environ.get("RS_NO_IPC"):
+        mine = torch.tensor(list(eng.ipc_export()), dtype=torch.uint8, device="cuda")
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        eng.ipc_import([bytes(h.cpu().tolist()) for h in allh])
     assert eng.run()
     st = eng.stats()
     rows = rs_trace.engine_rows(eng, 8)
@@ -49,8 +54,8 @@ def main():
         bad = rs_trace.compare(allrows, orows, state_mask=[0, 4, 5, 6, 7])
         tot = sum(g[2]["committed_events"] for g in gathered)
         late = sum(g[2]["late_events"] for g in gathered)
-        print("MULTIGPU_CHECK world=%d lps=%d T=%g committed=%d (oracle %d) windows=%s device_s=%s mismatches=%d %s" % (
-            world, n, T, tot, sum(r[0] for r in orows), [g[2]["windows"] for g in gathered],
+        print("MULTIGPU_CHECK exchange=%s world=%d lps=%d T=%g committed=%d (oracle %d) windows=%s device_s=%s mismatches=%d %s" % (
+            "nccl-sendrecv" if os.environ.get("RS_NO_IPC") else "nvlink-peer-push", world, n, T, tot, sum(r[0] for r in orows), [g[2]["windows"] for g in gathered],
             [round(g[2]["device_seconds"], 3) for g in gathered], len(bad), "PASS" if not bad else bad[:3]))
     dist.barrier()
     dist.destroy_process_group()
