@@ -174,6 +174,10 @@ def run_ours(args):
     e2e_steps = [one_step(True) for _ in range(max(1, min(args.steps, 2)))]
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    if rank == 0:
+        for tag, ss in (("step", steps), ("e2e", e2e_steps)):
+            for x in ss:
+                print("bench: %s device_s=%.4f wall_s=%.4f windows=%d" % (tag, x["device_s"], x["wall_s"], x["windows"]), file=sys.stderr)
 
     # one extra, untimed-for-the-metric step with CUDA events around EVERY kernel launch (RS_F_KTIME):
     # per-kernel device time for the roofline of the dominant kernel

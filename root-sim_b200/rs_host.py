@@ -45,7 +45,7 @@ class Config(C.Structure):
         ("max_pending", C.c_uint64), ("max_window", C.c_uint32), ("max_out", C.c_uint32),
         ("device", C.c_int32), ("topology_geometry", C.c_uint32), ("topology_out_of", C.c_uint32),
         ("hot_threshold", C.c_uint32), ("chain_target", C.c_uint32), ("rank", C.c_uint32), ("nranks", C.c_uint32),
-        ("xchg_cap", C.c_uint32), ("chunk_events", C.c_uint32),
+        ("xchg_cap", C.c_uint32), ("chunk_events", C.c_uint32), ("substeps", C.c_uint32), ("pad_cfg", C.c_uint32),
     ]
 
 
