@@ -187,3 +187,22 @@ def test_cli_executable(oracle_built, tmp_path):
     _, rows = rs_trace.parse_digest(str(tr))
     _, orows, _ = rs_trace.run_oracle("mixnet", 2000, sim_time=60, horizon=60, seed=42, extra=["--mean", "3.0"])
     assert rs_trace.compare(rows, orows) == []
+
+
+def test_time_stepped_big_lps_gpu(oracle_built):
+    """substeps (pause/resume of big LPs at checkpoint records, ordered arrival arrays kept across passes)"""
+    need("phold", oracle_built)
+    n, T = 262144, 30
+    rows, st = run_gpu("phold", n, T, window_events=1 << 20, arena_bytes=128, substeps=4, bucket_width=0.125)
+    _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+    assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
+
+
+def test_event_latency_probe(oracle_built):
+    """rs_dev_probe_event: the handler's serial latency on one device thread"""
+    need("phold", oracle_built)
+    lib = rs_host.build_model("phold")
+    with rs_host.Engine(lib, private=True) as eng:
+        eng.init(n_lps=1024, master_seed=1, simulation_time=10.0, max_out=1 << 18)
+        ns = eng.probe_event(5, 3, 2000, True)
+        assert 50.0 < ns < 20000.0
