@@ -15,13 +15,17 @@ import rs_trace  # noqa: E402
 def main():
     n = int(sys.argv[1])
     T = float(sys.argv[2])
+    over = dict(kv.split("=") for kv in sys.argv[3:])
     eng = rs_host.Engine(rs_host.build_model("pcs"))
     if os.environ.get("RS_DEBUG"):
         eng.lib.rs_set_debug(int(os.environ["RS_DEBUG"]))
     t0 = time.time()
-    eng.init(n_lps=n, master_seed=rs_trace.MASTER_SEED, simulation_time=T, window_events=1 << 20, arena_bytes=32768,
-             max_payload=48, bucket_width=0.25, n_buckets=4096, max_pending=256 * n + (1 << 20), flags=rs_host.RS_F_KTIME,
-             gvt_snapshot_cycles=1 << 30)
+    cfg = dict(n_lps=n, master_seed=rs_trace.MASTER_SEED, simulation_time=T, window_events=1 << 20, arena_bytes=32768,
+               max_payload=48, bucket_width=0.25, n_buckets=4096, max_pending=256 * n + (1 << 20), flags=rs_host.RS_F_KTIME,
+               gvt_snapshot_cycles=1 << 30)
+    for k, v in over.items():
+        cfg[k] = float(v) if k == "bucket_width" else int(v)
+    eng.init(**cfg)
     t1 = time.time()
     eng.run()
     t2 = time.time()
