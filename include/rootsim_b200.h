@@ -208,7 +208,7 @@ int rs_nccl_comm_destroy(void *comm);
  * other transports).  Engines of all ranks must be destroyed together (rs_dev_fini synchronises them). */
 #define RS_IPC_HANDLE_BYTES 64
 int rs_dev_ipc_export(rs_engine_t *e, void *handle64);
-int rs_dev_ipc_import(rs_engine_t *e, const void *handles /* nranks * RS_IPC_HANDLE_BYTES */);
+int rs_dev_ipc_import(rs_engine_t *e, const void *handles /* nranks * RS_IPC_HANDLE_BYTES; NULL = switch the direct exchange off again */);
 /* this rank's block of LPs under the reference's block distribution (src/core/core.c:275-300) */
 void rs_host_lp_block(uint32_t n_lps, uint32_t nranks, uint32_t rank, uint32_t *first, uint32_t *count);
 

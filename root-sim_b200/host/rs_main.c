@@ -193,11 +193,27 @@ int main(int argc, char **argv)
 	int finished = 0;
 	rs_stats_t st;
 	double last_print = 0;
+	/* rows of <output-dir>/thread_0_0/gvt (src/statistics/statistics.c:408-431): one per batch of windows */
+	struct gvt_row { double wct, gvt; unsigned committed, cumulated; } *gvt_rows = NULL;
+	size_t n_gvt_rows = 0, cap_gvt_rows = 0;
+	unsigned long long prev_committed = 0;
 	while (!finished) {
 		rc = rs_dev_run(eng, 64, &finished);
 		if (rc != RS_OK)
 			break;
 		rs_dev_stats(eng, &st);
+		if (n_gvt_rows == cap_gvt_rows) {
+			cap_gvt_rows = cap_gvt_rows ? 2 * cap_gvt_rows : 256;
+			gvt_rows = realloc(gvt_rows, cap_gvt_rows * sizeof *gvt_rows);
+		}
+		if (gvt_rows) {
+			gvt_rows[n_gvt_rows].wct = st.loop_seconds;
+			gvt_rows[n_gvt_rows].gvt = st.gvt;
+			gvt_rows[n_gvt_rows].committed = (unsigned)(st.committed_events - prev_committed);
+			gvt_rows[n_gvt_rows].cumulated = (unsigned)st.committed_events;
+			n_gvt_rows++;
+			prev_committed = st.committed_events;
+		}
 		if (verbose || st.loop_seconds - last_print >= 1.0) {
 			printf("TIME BARRIER %f - %llu committed events\n", st.gvt, (unsigned long long)st.committed_events);
 			fflush(stdout);
@@ -211,6 +227,20 @@ int main(int argc, char **argv)
 
 	mkdir(output_dir, 0755);
 	char path[1024];
+	snprintf(path, sizeof path, "%s/thread_0_0", output_dir);
+	mkdir(path, 0755);
+	snprintf(path, sizeof path, "%s/thread_0_0/gvt", output_dir);
+	FILE *fg = fopen(path, "w");
+	if (fg) {	/* same header and row format as print_gvt_stats_file() */
+		fprintf(fg, "#%15.15s    %15.15s    ", "\"WCT\"", "\"GVT VALUE\"");
+		fprintf(fg, "%15.15s    %15.15s\n", "\"EVENTS\"", "\"CUMUL EVENTS\"");
+		for (size_t i = 0; i < n_gvt_rows; i++) {
+			fprintf(fg, " %15lf    %15lf    ", gvt_rows[i].wct, gvt_rows[i].gvt);
+			fprintf(fg, "%15u    %15u\n", gvt_rows[i].committed, gvt_rows[i].cumulated);
+		}
+		fclose(fg);
+	}
+	free(gvt_rows);
 	snprintf(path, sizeof path, "%s/execution_stats", output_dir);
 	FILE *f = fopen(path, "w");
 	if (f) {

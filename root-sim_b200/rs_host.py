@@ -249,8 +249,11 @@ class Engine:
 
     def ipc_import(self, handles):
         """handles: the nranks exported handles in rank order"""
-        blob = b"".join(handles)
-        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        if handles is None:
+            buf = None
+        else:
+            blob = b"".join(handles)
+            buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
         rc = self.lib.rs_dev_ipc_import(self.h, buf)
         if rc != 0:
             raise RsError(rc, self.lib.rs_dev_error(self.h).decode())

@@ -196,6 +196,10 @@ def test_cli_executable_emu(oracle_built, tmp_path):
                         "--b200-arena-bytes", "1024", "--b200-max-payload", "16", "--b200-bucket-width", "0.25",
                         "--output-dir", str(out), "--b200-trace", str(tr), "--mean", "3.0"], capture_output=True, text=True)
     assert r.returncode == 0 and "SIMULATION CORRECTLY COMPLETED" in r.stdout
+    gvt = open(out / "thread_0_0" / "gvt").read().split("\n")          # statistics.c:408-431
+    assert gvt[0].split() == ['#', '"WCT"', '"GVT', 'VALUE"', '"EVENTS"', '"CUMUL', 'EVENTS"'] or '"GVT VALUE"' in gvt[0]
+    rows_g = [l.split() for l in gvt[1:] if l.strip()]
+    assert rows_g and all(len(r) == 4 for r in rows_g) and int(rows_g[-1][3]) == sum(int(r[2]) for r in rows_g)
     stats = open(out / "execution_stats").read()
     for label in ("TOTAL EXECUTED EVENTS", "TOTAL COMMITTED EVENTS", "TOTAL ROLLBACKS EXECUTED", "TOTAL ANTIMESSAGES", "EFFICIENCY", "LAST COMMITTED GVT"):
         assert label in stats
