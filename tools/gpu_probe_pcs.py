@@ -16,7 +16,7 @@ def main():
     n = int(sys.argv[1])
     T = float(sys.argv[2])
     over = dict(kv.split("=") for kv in sys.argv[3:])
-    eng = rs_host.Engine(rs_host.build_model("pcs"))
+    eng = rs_host.Engine(os.environ.get("RS_LIB") or rs_host.build_model("pcs"))
     if os.environ.get("RS_DEBUG"):
         eng.lib.rs_set_debug(int(os.environ["RS_DEBUG"]))
     t0 = time.time()
