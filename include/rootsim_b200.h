@@ -90,7 +90,8 @@ typedef struct rs_config {
 	uint32_t xchg_cap;		/* records per peer and exchange step (0 = 65536)                   */
 	uint32_t chunk_events;		/* optional: an LP pauses after this many events per pass (0 = off)      */
 	uint32_t substeps;		/* LPs with a big group walk through a window in this many time steps, one
-					 * per straggler round (0 = engine default, 1 = off)                     */
+					 * per straggler round (0 = engine default, 1 = off, 0x7fffffff = "defer":
+					 * nothing in the first pass, everything in the second)                  */
 	uint32_t pad_cfg;
 } rs_config_t;
 

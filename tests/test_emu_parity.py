@@ -237,7 +237,7 @@ def test_chunked_execution_and_checkpoint_ring(oracle_built, chunk, period):
         assert st.rollbacks > 0
 
 
-@pytest.mark.parametrize("substeps,bw", [(4, 0.0), (8, 0.125), (3, 0.5)])
+@pytest.mark.parametrize("substeps,bw", [(4, 0.0), (8, 0.125), (3, 0.5), (0x7fffffff, 0.0)])     # last: the "defer" policy
 def test_time_stepped_big_lps(oracle_built, substeps, bw):
     """substeps > 1: LPs with a big group stop at a time limit that moves on once per straggler round (pause at a
     checkpoint record in front of the first event beyond the limit, resume in the next pass, roll back when the
