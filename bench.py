@@ -338,7 +338,7 @@ def run_reference(args):
     emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "events/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (t1 - t0) / max(1, args.steps + args.warmup),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "models/phold on the host CPU: " + cb["sample"]},
         "cpu_baseline": cb, "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
