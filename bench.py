@@ -75,10 +75,12 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def phold_cfg(n_lps, sim_time):
+def phold_cfg(n_lps, sim_time, world=1):
     """Pool sizing for shipped PHOLD (population grows ~ N*0.9*e^{0.04 t})."""
     import math
     pending = int(n_lps * (1.0 * math.exp(0.04 * sim_time) + 1.0) * 1.25) + (1 << 20)
+    if world > 1:       # max_pending sizes ONE rank's pool: its share of the population, plus room for the uneven hot LPs
+        pending = int(pending / world * 1.5) + (1 << 20)
     # Per-LP seeds repeat every 64 gids (src/lib/numerical.c:399-409), so n_lps/64 "twin" LPs fire together
     # and create hot LPs that receive about n_lps/64 times the average load.  Size the calendar bucket so
     # that the hottest LP sees about a thousand events per bucket at the end of the run.
@@ -105,7 +107,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib_path = rs_host.build_model("phold")
     n_lps, T = args.lps, args.sim_time
-    cfg = phold_cfg(n_lps, T)
+    cfg = phold_cfg(n_lps, T, world)
     cfg["device"] = local
     lib = rs_host.load(lib_path)
     first, count = rs_host.lp_block(lib, n_lps, world, rank)
@@ -144,27 +146,29 @@ def run_ours(args):
         if int(flag[0]) == 0:       # every rank takes the same path
             eng.ipc_import(None)
 
-    def one_step(e2e):
+    import rs_trace
+
+    def one_step(e2e, cfg=cfg, seeds=seeds, first=first, count=count):
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
         t0 = time.perf_counter()
         eng = rs_host.Engine(lib_path)
-        eng.init(host_seeds=seeds if e2e else None, **cfg)
+        # the end-to-end steps carry the committed-trace digests (RS_F_TRACE: per-LP event hash) and are checked
+        # against the oracle's golden checksum of this very configuration
+        eng.init(host_seeds=seeds if e2e else None, **(dict(cfg, flags=rs_host.RS_F_TRACE) if e2e else cfg))
         if world > 1:
             eng.set_nccl_comm(comm)
             connect_peers(eng)
         fin = eng.run()
         st = eng.stats()
-        tr = eng.trace() if e2e else None
+        cs = rs_trace.checksum_engine(eng, first) if e2e else None      # D2H of the per-LP digests + checksum on the host
         t1 = time.perf_counter()
         assert fin and (st.status & ~0x1) == 0, st.as_dict()
         committed = st.committed_events - count       # INIT events are processed at engine creation
         res = dict(committed=committed, device_s=st.device_seconds, wall_s=t1 - t0, launches=st.kernel_launches,
                    windows=st.windows, rollbacks=st.rollbacks, executed=st.executed_events, silent=st.silent_events,
                    rounds=st.relax_rounds, late=st.late_events, antimessages=st.antimessages)
-        if e2e:
-            res["count_sum"] = sum(tr[i].count for i in range(0, count, max(1, count // 4096)))
         eng.fini()
         if world > 1:
             v = torch.tensor([res["device_s"], res["wall_s"]], dtype=torch.float64, device="cuda")
@@ -173,7 +177,24 @@ def run_ours(args):
             dist.all_reduce(c, op=dist.ReduceOp.SUM)
             res["device_s"], res["wall_s"] = float(v[0]), float(v[1])
             res["committed"], res["launches"] = float(c[0]), float(c[1])
+        if e2e:
+            # partial checksums of the ranks' LP blocks add up (mod 2^64) to the checksum of the whole trace
+            parts = [cs]
+            if world > 1:
+                parts = [None] * world
+                dist.all_gather_object(parts, cs)
+            res["checksum"] = sum(p[0] for p in parts) & 0xFFFFFFFFFFFFFFFF
+            res["traced"] = sum(p[1] for p in parts)
         return res
+
+    def check_parity(res, n, T):
+        """compare with tests/golden/phold_checksums.json (oracle run of exactly this configuration); None = no golden"""
+        gp = os.path.join(REPO, "tests", "golden", "phold_checksums.json")
+        gold = json.load(open(gp)).get("phold_lp%d_T%g" % (n, T)) if os.path.exists(gp) else None
+        if gold is None:
+            return None, None
+        ok = ("%016x" % res["checksum"]) == gold["checksum"] and res["traced"] == gold["traced_events_incl_init"]
+        return ok, gold
 
     for _ in range(args.warmup):
         one_step(False)
@@ -242,6 +263,28 @@ def run_ours(args):
                         "hbm_frac_whole_loop": B_ALG_PHOLD * v / 1e9 / measured_peak()[0]}
         sup = dict(best, workload="models/phold, %d LPs, T=%g, one DISTINCT seed per LP (host seed array): no twin LPs" % (n_lps, T))
 
+    parity_ok, gold = None, None
+    for x in e2e_steps:
+        ok, gold = check_parity(x, n_lps, T)
+        parity_ok = ok if parity_ok is None else (parity_ok and ok)
+
+    # BASELINE.json configs[3] (C4): PHOLD with 16,777,216 LPs on 2/4/8 GPUs, --simulation-time 60, one checked step
+    secondary = None
+    if world > 1 and not args.no_c4:
+        n4, T4 = 1 << 24, 60.0
+        cfg4 = phold_cfg(n4, T4, world)
+        f4, c4 = rs_host.lp_block(lib, n4, world, rank)
+        cfg4.update(device=local, rank=rank, nranks=world, lp_first=f4, lp_count=c4)
+        r4 = one_step(True, cfg=cfg4, seeds=rs_host.lp_seeds(lib, MASTER_SEED, f4, c4), first=f4, count=c4)
+        ok4, gold4 = check_parity(r4, n4, T4)
+        secondary = {"metric": "committed events/sec (PHOLD 16M LPs, BASELINE configs[3])", "value": r4["committed"] / r4["device_s"],
+                     "unit": "events/s", "lps": n4, "simulation_time": T4, "committed_events": r4["committed"], "device_s": r4["device_s"],
+                     "e2e_value": r4["committed"] / r4["wall_s"], "windows": r4["windows"], "rollbacks": r4["rollbacks"],
+                     "parity_checksum_ok": ok4, "checksum": "%016x" % r4["checksum"],
+                     "hbm_frac_whole_loop": B_ALG_PHOLD * r4["committed"] / r4["device_s"] / 1e9 / measured_peak()[0] / world}
+        if rank == 0:
+            print("bench: C4 16M LPs device_s=%.3f wall_s=%.3f parity=%s" % (r4["device_s"], r4["wall_s"], ok4), file=sys.stderr)
+
     dev_s = sum(s["device_s"] for s in steps)          # already the max over ranks per step
     committed = sum(s["committed"] for s in steps)      # already summed over ranks
     value = committed / dev_s
@@ -281,9 +324,18 @@ def run_ours(args):
                              "reference workload), one GPU thread at ~1.4 us per event; see DESIGN.md section 5"},
         "kernel_ms": {k: round(v[0], 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])},
         "clocks": sampler.summary(),
+        "parity_checksum_ok": parity_ok,
+        "parity": {"checksum": "%016x" % e2e_steps[0]["checksum"], "golden": gold["checksum"] if gold else None,
+                   "traced_events": e2e_steps[0]["traced"], "golden_traced_events": gold["traced_events_incl_init"] if gold else None,
+                   "what": "order-independent 64-bit checksum over every LP's (gid, committed event count, FNV hash of its "
+                           "(timestamp bits, type) sequence, last timestamp bits, RNG seed), computed from the device digests of "
+                           "the end-to-end steps and compared with the CPU oracle's checksum for this configuration "
+                           "(tests/golden/phold_checksums.json, tests/golden/make_checksums.py)"},
     }
     if sup:
         line["supplementary"] = sup
+    if secondary:
+        line["secondary"] = secondary
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(1)
@@ -291,6 +343,9 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity_ok is False or (secondary and secondary["parity_checksum_ok"] is False):
+        print("bench.py: PARITY CHECKSUM MISMATCH against the oracle", file=sys.stderr)
+        sys.exit(3)
 
 
 def cpu_baseline(runs):
@@ -364,6 +419,7 @@ def main():
     ap.add_argument("--sim-time", type=float, default=100.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-supplementary", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 16M-LP secondary run of the multi-GPU bench")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,49 @@
+#!/usr/bin/env python3
+"""Golden checksums of the configurations bench.py times (BASELINE.json configs[1] and configs[3]).
+
+Runs the CPU oracle oracle/_build/seqp_phold (rs_math.h log: bit-identical with the device build) on the
+exact bench configuration and stores the order-independent checksum of the per-LP committed-trace digests
+(tests/rs_trace.py::checksum_arrays) in phold_checksums.json.  bench.py recomputes the same checksum from
+the device engine's digests in its end-to-end steps, at every GPU count, and fails on a mismatch.
+
+  python tests/golden/make_checksums.py                 # 1,048,576 LPs, T=100  (~8 min, 5 GB)
+  python tests/golden/make_checksums.py 16777216 60     # 16,777,216 LPs, T=60  (~45 min, 25 GB)
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import rs_trace  # noqa: E402
+
+OUT = os.path.join(HERE, "phold_checksums.json")
+
+
+def key(n, T):
+    return "phold_lp%d_T%g" % (n, T)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+    T = float(sys.argv[2]) if len(sys.argv) > 2 else 100.0
+    digest = sys.argv[3] if len(sys.argv) > 3 else None      # an existing digest file of exactly this run
+    exe = os.path.join(rs_trace.ORACLE_BUILD, "seqp_phold")
+    with tempfile.TemporaryDirectory() as td:
+        if digest is None:
+            digest = os.path.join(td, "trace.txt")
+            env = dict(os.environ, RS_TRACE_OUT=digest, RS_TRACE_HORIZON=repr(T))
+            subprocess.run([exe, "--lp", str(n), "--seed", str(rs_trace.MASTER_SEED), "--simulation-time", repr(T)], env=env, check=True)
+        cs, total = rs_trace.checksum_digest_file(digest)
+    db = json.load(open(OUT)) if os.path.exists(OUT) else {}
+    db[key(n, T)] = {"model": "phold", "n_lps": n, "simulation_time": T, "master_seed": rs_trace.MASTER_SEED,
+                     "oracle": "oracle/seqsim.c, rs_math.h log (seqp_phold)", "committed_events": total - n,
+                     "traced_events_incl_init": total, "checksum": "%016x" % cs}
+    json.dump(db, open(OUT, "w"), indent=1, sort_keys=True)
+    print(key(n, T), db[key(n, T)])
+
+
+if __name__ == "__main__":
+    main()

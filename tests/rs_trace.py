@@ -112,3 +112,61 @@ def compare(rows_a, rows_b, state_mask=None, ts_ulp=0, check_hash=True):
             bad.append("...")
             break
     return bad
+
+
+# ---------------------------------------------------------------------------------------------------
+# Order-independent 64-bit checksum of a committed trace: sum over LPs (mod 2^64) of a splitmix64 chain over
+# (global LP id, event count, event hash, last timestamp bits, RNG seed).  Partial sums over disjoint LP
+# blocks add up, so every rank of a multi-GPU run checksums its own block and the sums are all-reduced.
+# bench.py compares it with tests/golden/phold_checksums.json (made by tests/golden/make_checksums.py from
+# the CPU oracle) for the exact configuration it times.
+def _splitmix64(x):
+    import numpy as np
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def checksum_arrays(counts, hashes, ts_bits, seeds, first_gid=0):
+    """-> (checksum, total count); all inputs are array-likes of unsigned 64-bit integers of one LP block."""
+    import numpy as np
+    with np.errstate(over="ignore"):
+        c = np.asarray(counts, dtype=np.uint64)
+        g = np.arange(first_gid, first_gid + len(c), dtype=np.uint64)
+        x = _splitmix64(np.asarray(seeds, dtype=np.uint64))
+        x = _splitmix64(x ^ np.asarray(ts_bits, dtype=np.uint64))
+        x = _splitmix64(x ^ np.asarray(hashes, dtype=np.uint64))
+        x = _splitmix64(x ^ c)
+        x = _splitmix64(x ^ g)
+        return int(x.sum(dtype=np.uint64)), int(c.sum(dtype=np.uint64))
+
+
+def checksum_rows(rows, first_gid=0):
+    """checksum of digest rows as returned by parse_digest() / engine_rows()"""
+    return checksum_arrays([r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows], [r[3] for r in rows], first_gid)
+
+
+def checksum_engine(eng, first_gid=0):
+    """checksum of a device engine's per-LP digests (one D2H copy of 32 bytes per LP through rs_dev_trace)"""
+    import numpy as np
+    tr = eng.trace()
+    a = np.frombuffer(tr, dtype=np.dtype([("count", "<u8"), ("hash", "<u8"), ("ts", "<u8"), ("seed", "<u8")]))
+    return checksum_arrays(a["count"], a["hash"], a["ts"], a["seed"], first_gid)
+
+
+def checksum_digest_file(path):
+    """checksum of a digest file written by the oracle, without building Python tuples (16M-LP files)"""
+    import numpy as np
+    cols = [[], [], [], []]
+    with open(path) as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            p = line.split()
+            cols[0].append(int(p[1]))
+            cols[1].append(int(p[2], 16))
+            cols[2].append(int(p[3], 16))
+            cols[3].append(int(p[4], 16))
+    return checksum_arrays(*[np.array(c, dtype=np.uint64) for c in cols])

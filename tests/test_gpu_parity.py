@@ -16,9 +16,12 @@ PHOLD_MASK = [0, 4, 5, 6, 7]
 
 def run_gpu(model, n, T, margs=(), state_bytes=8, seed=rs_trace.MASTER_SEED, **cfg):
     lib = rs_host.build_model(model)
-    with rs_host.Engine(lib, private=True) as eng:
+    # model options live in file-scope variables of the library: only a run that sets them needs a private
+    # copy; everything else loads the in-tree root-sim_b200/_built/lib<model>.so itself
+    with rs_host.Engine(lib, private=bool(margs)) as eng:
         assert eng.info().engine == b"cuda-sm100a"
-        eng.model_args(list(margs))
+        if margs:
+            eng.model_args(list(margs))
         eng.init(n_lps=n, master_seed=seed, simulation_time=T, **cfg)
         assert eng.run()
         st = eng.stats()
@@ -202,7 +205,7 @@ def test_event_latency_probe(oracle_built):
     """rs_dev_probe_event: the handler's serial latency on one device thread"""
     need("phold", oracle_built)
     lib = rs_host.build_model("phold")
-    with rs_host.Engine(lib, private=True) as eng:
+    with rs_host.Engine(lib) as eng:
         eng.init(n_lps=1024, master_seed=1, simulation_time=10.0, max_out=1 << 18)
         ns = eng.probe_event(5, 3, 2000, True)
         assert 50.0 < ns < 20000.0
