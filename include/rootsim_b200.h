@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 1
+#define RS_ABI_VERSION 2
 
 /* error codes (reference: rootsim_error(fatal=true) -> exit(EXIT_FAILURE), src/core/core.c:220-250) */
 enum {
@@ -49,9 +49,10 @@ enum {
 #define RS_ST_PAYLOAD		0x0400u	/* event payload larger than max_payload                        */
 #define RS_ST_NO_EVENTS		0x0800u	/* pending set became empty before the horizon                  */
 #define RS_ST_XCHG_FULL		0x1000u	/* inter-rank exchange slot exhausted (raise xchg_cap)          */
+#define RS_ST_PEER_FATAL	0x2000u	/* another rank stopped with a fatal status (its own bits say why) */
 #define RS_ST_FATAL_MASK	(RS_ST_PAST_EVENT | RS_ST_RESERVED_TYPE | RS_ST_MODEL_EXIT | RS_ST_ARENA_FULL | \
 				 RS_ST_POOL_FULL | RS_ST_WINDOW_FULL | RS_ST_OUT_FULL | RS_ST_HORIZON | RS_ST_LATE_FULL | RS_ST_PAYLOAD | \
-				 RS_ST_XCHG_FULL)
+				 RS_ST_XCHG_FULL | RS_ST_PEER_FATAL)
 
 /* engine flags */
 #define RS_F_TRACE		0x1u	/* keep the per-LP committed-trace digest (count/hash/last ts)   */
@@ -69,7 +70,8 @@ typedef struct rs_config {
 	uint32_t lp_count;		/*   src/core/core.c:275-300); lp_count==0 means all n_lps        */
 	uint64_t master_seed;		/* ~/.rootsim/numerical.conf value (src/lib/numerical.c:326-391)   */
 	double simulation_time;		/* --simulation-time; 0 = run until OnGVT says stop                */
-	uint32_t ckpt_period;		/* --p (accepted; checkpoints are taken per LP per window)         */
+	uint32_t ckpt_period;		/* --p: an LP takes a checkpoint at its first event of a window and then every
+					 * ckpt_period events inside it (src/mm/state.c:55-130)            */
 	uint32_t gvt_snapshot_cycles;	/* --gvt-snapshot-cycles: OnGVT termination check every N windows  */
 	double bucket_width;		/* calendar bucket width in simulated time (power of two)          */
 	uint32_t n_buckets;		/* calendar ring size (power of two)                               */
@@ -83,16 +85,20 @@ typedef struct rs_config {
 	int32_t device;			/* CUDA device ordinal                                             */
 	uint32_t topology_geometry;	/* filled from the model's topology_settings by rs_model_info()    */
 	uint32_t topology_out_of;	/*   .out_of_topology                                              */
-	uint32_t hot_threshold;		/* LPs with more events than this in one window run last (0 = off)  */
-	uint32_t chain_target;		/* optimism control: wanted largest per-LP group per window (0=8192) */
+	uint32_t hot_threshold;		/* an LP with more window events than this is a "chain LP": it gets a warp of its own
+					 * and stays one pacing step behind the others (0 = 256)                 */
+	uint32_t chain_target;		/* unused since ABI 2 (the window width no longer bounds optimism)  */
 	uint32_t rank;			/* this engine's rank and the number of ranks (one engine per GPU);  */
 	uint32_t nranks;		/*   nranks <= 1 means a single engine owning every LP              */
 	uint32_t xchg_cap;		/* records per peer and exchange step (0 = 65536)                   */
-	uint32_t chunk_events;		/* optional: an LP pauses after this many events per pass (0 = off)      */
-	uint32_t substeps;		/* LPs with a big group walk through a window in this many time steps, one
-					 * per straggler round (0 = engine default, 1 = off, 0x7fffffff = "defer":
-					 * nothing in the first pass, everything in the second)                  */
-	uint32_t pad_cfg;
+	uint32_t chunk_events;		/* event budget of one visit of an LP: after this many events it stops and goes on
+					 * in the next pacing round, while the other LPs move on (0 = 1024)      */
+	uint32_t substeps;		/* pacing steps per window: the time limit below which LPs execute moves from the
+					 * window start to its end in this many rounds (0 = chosen per window so that a
+					 * step holds about one event per LP; 1 = no pacing inside a window)     */
+	uint32_t pace_trail;		/* chain LPs stay one pacing step behind: 0/1 = yes (default), 2 = no   */
+	double window_span;		/* widest optimistic window in simulated time (0 = no limit besides
+					 * window_events and 64 calendar buckets)                               */
 } rs_config_t;
 
 /* Aggregate counters; definitions follow src/statistics/statistics.h:87-103 and :345-349. */
@@ -161,8 +167,8 @@ void rs_host_lp_seeds(uint64_t master_seed, uint32_t lp_first, uint32_t lp_count
 int rs_dev_init(const rs_config_t *cfg, const uint64_t *host_seeds, rs_engine_t **out);
 
 /* Advance the simulation by at most max_windows optimistic windows (0 = until termination).
- * One window = select -> group -> execute -> straggler rounds (rollback, coast-forward, cancel) ->
- * commit (GVT, fossil collection).  Replaces the body of main_simulation_loop
+ * One window = select -> group -> pacing rounds (wake, execute / roll back / coast-forward / cancel,
+ * deliver) until nothing is left below the window end -> commit (GVT, fossil collection).  Replaces the body of main_simulation_loop
  * (src/main.c:132-170: process_bottom_halves, schedule, gvt_operations).
  * Returns RS_OK and sets *finished (may be NULL) when end_computing() (src/main.c:67-87) holds. */
 int rs_dev_run(rs_engine_t *e, uint64_t max_windows, int *finished);

@@ -4,7 +4,7 @@
  *
  * CPU restatement of the reference's SEQUENTIAL engine and of the library calls a model makes on
  * the hot path, small enough to run 1M+ LPs (the real reference cannot: MAX_LPs 250000, 4 MiB stack
- * per LP, O(#LP) lookup per event -- SURVEY.md top).  Parity is PINNED: tests/test_oracle_vs_ref.py
+ * per LP, O(#LP) lookup per event -- SURVEY.md top).  Parity is PINNED: tests/test_oracle.py
  * compares its per-LP trace digest bit-exactly with the unmodified reference built by
  * oracle/build_ref.sh (oracle/_ref/<model>_trace) and with the committed fixtures in tests/golden/.
  *
@@ -553,6 +553,9 @@ int main(int argc, char **argv)
 			}
 		}
 	}
+	const char *mp = getenv("RS_ORACLE_MAX_PAYLOAD");	/* event records are pooled at this payload size: 0 for
+								 * payload-free models makes 16M-LP runs fit in memory */
+	if (mp) max_payload = (unsigned)atoi(mp);
 	const char *h = getenv("RS_TRACE_HORIZON");
 	if (h) horizon = atof(h);
 	const char *sb = getenv("RS_TRACE_STATE_BYTES");

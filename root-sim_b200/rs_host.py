@@ -16,14 +16,14 @@ REPO = os.path.dirname(HERE)
 BUILT = os.path.join(HERE, "_built")
 ROOTSIM_CC = os.path.join(HERE, "bin", "rootsim-cc")
 
-RS_ABI_VERSION = 1
+RS_ABI_VERSION = 2
 RS_F_TRACE = 0x1
 RS_F_KTIME = 0x2
 
 STATUS_BITS = {
     0x0001: "BAD_RECEIVER", 0x0002: "PAST_EVENT", 0x0004: "RESERVED_TYPE", 0x0008: "MODEL_EXIT",
     0x0010: "ARENA_FULL", 0x0020: "POOL_FULL", 0x0040: "WINDOW_FULL", 0x0080: "OUT_FULL",
-    0x0100: "HORIZON", 0x0200: "LATE_FULL", 0x0400: "PAYLOAD", 0x0800: "NO_EVENTS", 0x1000: "XCHG_FULL",
+    0x0100: "HORIZON", 0x0200: "LATE_FULL", 0x0400: "PAYLOAD", 0x0800: "NO_EVENTS", 0x1000: "XCHG_FULL", 0x2000: "PEER_FATAL",
 }
 ERRORS = {0: "RS_OK", 1: "RS_ERR_NO_DEVICE", 2: "RS_ERR_BAD_CONFIG", 3: "RS_ERR_OOM", 4: "RS_ERR_CUDA",
           5: "RS_ERR_MODEL", 6: "RS_ERR_CAPACITY"}
@@ -45,7 +45,8 @@ class Config(C.Structure):
         ("max_pending", C.c_uint64), ("max_window", C.c_uint32), ("max_out", C.c_uint32),
         ("device", C.c_int32), ("topology_geometry", C.c_uint32), ("topology_out_of", C.c_uint32),
         ("hot_threshold", C.c_uint32), ("chain_target", C.c_uint32), ("rank", C.c_uint32), ("nranks", C.c_uint32),
-        ("xchg_cap", C.c_uint32), ("chunk_events", C.c_uint32), ("substeps", C.c_uint32), ("pad_cfg", C.c_uint32),
+        ("xchg_cap", C.c_uint32), ("chunk_events", C.c_uint32), ("substeps", C.c_uint32), ("pace_trail", C.c_uint32),
+        ("window_span", C.c_double),
     ]
 
 

@@ -75,8 +75,8 @@ def test_pcs_mutual_zero_delay_cycle(oracle_built):
 
 def test_hot_lp_path(oracle_built):
     """Twin LPs (same seed every 64 gids, src/lib/numerical.c:399-409) fire together and create LPs with
-    hundreds of events per window: exercises the deferred hot-LP phase, the cooperative sort of large
-    groups, the spill heap for in-window self events and long in-window arrival lists."""
+    hundreds of events per window: exercises the chain-LP path (own warp, one pacing step behind), the
+    cooperative sort of large groups, the heap for in-window self events and long in-window arrival lists."""
     if not rs_host.model_sources("phold") or not os.path.exists(os.path.join(oracle_built, "seqp_phold")):
         pytest.skip("phold sources live in the reference tree")
     n, T = 16384, 30
@@ -214,10 +214,10 @@ def test_cli_executable_emu(oracle_built, tmp_path):
 # ---------------------------------------------------------------- checkpoint ring and chunked execution
 @pytest.mark.parametrize("chunk,period", [(1, 1), (2, 3), (5, 2), (3, 1000000)])
 def test_chunked_execution_and_checkpoint_ring(oracle_built, chunk, period):
-    """Tiny chunk_events / ckpt_period force every LP to pause after a few events and to take in-window
-    checkpoints constantly: resume-after-pause, rollback to a ring record, rollback of a paused LP, the
-    own-pending-events snapshot in the records, and annihilation of self-addressed events at rollback are
-    all exercised on three models; the committed trace must not change."""
+    """Tiny chunk_events / ckpt_period force every LP to stop after a few events per visit and to take in-window
+    checkpoints constantly: going on from the window-local position, rollback to a checkpoint record, rollback of
+    an LP that stopped in the middle, the own-pending-events snapshot in the records, and annihilation of
+    self-addressed events at rollback are all exercised on three models; the committed trace must not change."""
     cases = [("mixnet", 300, 150, ["--token-prob", "0.9"], 32, dict(seed=42),
               dict(master_seed=42, window_events=2000, arena_bytes=1024, max_payload=16, bucket_width=0.25), None)]
     if rs_host.model_sources("phold") and os.path.exists(os.path.join(oracle_built, "seqp_phold")):
@@ -237,21 +237,37 @@ def test_chunked_execution_and_checkpoint_ring(oracle_built, chunk, period):
         assert st.rollbacks > 0
 
 
-@pytest.mark.parametrize("substeps,bw", [(4, 0.0), (8, 0.125), (3, 0.5), (0x7fffffff, 0.0)])     # last: the "defer" policy
-def test_time_stepped_big_lps(oracle_built, substeps, bw):
-    """substeps > 1: LPs with a big group stop at a time limit that moves on once per straggler round (pause at a
-    checkpoint record in front of the first event beyond the limit, resume in the next pass, roll back when the
-    new input lies below the pause point); long in-window arrival lists are kept ordered across passes and only
-    the new arrivals are merged in.  The committed trace must not change."""
+@pytest.mark.parametrize("substeps,bw,trail,hot", [(4, 0.0, 1, 0), (8, 0.125, 2, 40), (3, 0.5, 1, 8), (64, 0.0, 1, 100), (1, 0.0, 1, 0)])
+def test_paced_rounds(oracle_built, substeps, bw, trail, hot):
+    """Pacing inside a window: the time limit moves from the window start to its end in `substeps` rounds, every LP
+    stops in front of the first event beyond it and goes on in a later round from its window-local position; chain
+    LPs (hot_threshold) stay one step behind (pace_trail).  A straggler below the position an LP stopped at rolls it
+    back; long in-window arrival lists are kept ordered across visits and only the new arrivals are merged in.  The
+    committed trace must not depend on any of it."""
     if not rs_host.model_sources("phold") or not os.path.exists(os.path.join(oracle_built, "seqp_phold")):
         pytest.skip("phold sources live in the reference tree")
     n, T = 65536, 30
-    cfg = dict(arena_bytes=128, substeps=substeps, ckpt_period=3)
+    cfg = dict(arena_bytes=128, substeps=substeps, ckpt_period=3, pace_trail=trail, hot_threshold=hot)
     if bw:
         cfg["bucket_width"] = bw
     rows, st = run_emu("phold", n, T, 1 << 20, **cfg)
     _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
     assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
-    base_rows, base = run_emu("phold", n, T, 1 << 20, arena_bytes=128, **({"bucket_width": bw} if bw else {}))
-    assert st.relax_rounds > base.relax_rounds          # the extra passes really happened
     assert st.rollbacks > 0
+    if substeps > 1:
+        base_rows, base = run_emu("phold", n, T, 1 << 20, arena_bytes=128, substeps=1, **({"bucket_width": bw} if bw else {}))
+        assert st.relax_rounds >= base.relax_rounds
+        assert rs_trace.compare(rows, base_rows, state_mask=PHOLD_MASK) == []
+
+
+def test_wide_window_with_lagging_lps(oracle_built):
+    """One window spanning the whole run (16 simulated time units, 64 buckets of 0.25), paced in many rounds, tiny
+    event budget per visit: the LPs that receive the twin bursts fall far behind the limit while the others go on;
+    what they send later arrives as stragglers everywhere."""
+    if not rs_host.model_sources("phold") or not os.path.exists(os.path.join(oracle_built, "seqp_phold")):
+        pytest.skip("phold sources live in the reference tree")
+    n, T = 32768, 16
+    rows, st = run_emu("phold", n, T, 1 << 22, arena_bytes=128, bucket_width=0.25, chunk_events=16, hot_threshold=32, max_pending=4 << 20)
+    _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+    assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
+    assert st.windows <= 3 and st.rollbacks > 0 and st.relax_rounds > 32
