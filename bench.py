@@ -76,20 +76,22 @@ class ClockSampler(threading.Thread):
 
 
 def phold_cfg(n_lps, sim_time, world=1):
-    """Pool sizing for shipped PHOLD (population grows ~ N*0.9*e^{0.04 t})."""
+    """Pool sizing for shipped PHOLD (population grows ~ N*0.9*e^{0.04 t}).
+    Windows are WIDE (up to 4 simulated time units, 64 calendar buckets of 1/16): inside a window the engine
+    paces the LPs in rounds, so an LP that receives a same-timestamp burst from its n_lps/64 twin senders
+    (src/lib/numerical.c:399-409: only 64 distinct seeds) falls behind without stopping the others, and has the
+    rest of the window to catch up."""
     import math
     pending = int(n_lps * (1.0 * math.exp(0.04 * sim_time) + 1.0) * 1.25) + (1 << 20)
+    rate = 0.04 * 5.0 * n_lps * math.exp(0.04 * sim_time)          # events per simulated time unit at the end of the run
     if world > 1:       # max_pending sizes ONE rank's pool: its share of the population, plus room for the uneven hot LPs
         pending = int(pending / world * 1.5) + (1 << 20)
-    # Per-LP seeds repeat every 64 gids (src/lib/numerical.c:399-409), so n_lps/64 "twin" LPs fire together
-    # and create hot LPs that receive about n_lps/64 times the average load.  Size the calendar bucket so
-    # that the hottest LP sees about a thousand events per bucket at the end of the run.
-    hot_rate = (n_lps / 64.0) * 0.2 * math.exp(0.04 * sim_time)
-    bw = 0.0625
-    while hot_rate * bw > 1024 and bw > 1.0 / 1024:
-        bw /= 2
-    return dict(n_lps=n_lps, master_seed=MASTER_SEED, simulation_time=float(sim_time), window_events=1 << 20,
-                arena_bytes=128, max_pending=pending, bucket_width=bw, n_buckets=max(4096, int(160 / bw)),
+        rate = rate / world * 1.5
+    span = 4.0
+    win = int(rate * span * 1.1) + (1 << 20)                     # events of the widest window (those already pending when it starts)
+    return dict(n_lps=n_lps, master_seed=MASTER_SEED, simulation_time=float(sim_time), window_events=win,
+                max_window=win + (win >> 2), max_out=2 * win + (1 << 22), window_span=span,
+                arena_bytes=128, max_pending=pending, bucket_width=0.0625, n_buckets=4096,
                 gvt_snapshot_cycles=1 << 30, flags=0)
 
 
@@ -248,7 +250,7 @@ def run_ours(args):
         hi = (z >> np.uint64(32)) % np.uint64(0x464FFFFE) + np.uint64(1)
         dseeds = ((hi << np.uint64(32)) | lo).astype(np.uint64)
         arr = (C.c_uint64 * n_lps).from_buffer(dseeds)
-        scfg = dict(cfg, bucket_width=0.0625, n_buckets=4096)
+        scfg = dict(cfg)
         best = None
         for _ in range(2):
             eng = rs_host.Engine(lib_path)

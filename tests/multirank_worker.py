@@ -43,11 +43,18 @@ def main():
     cfg = dict(spec["cfg"], n_lps=spec["n"], rank=rank, nranks=world, lp_first=first, lp_count=count)
     eng.init(**cfg)
     eng.set_comm(make_comm(world))
-    assert eng.run()
+    err = None
+    try:
+        assert eng.run()
+    except rs_host.RsError as ex:
+        if not spec.get("expect_error"):
+            raise
+        err = ex.code
     st = eng.stats()
-    rows = rs_trace.engine_rows(eng, spec["state_bytes"])
+    rows = rs_trace.engine_rows(eng, spec["state_bytes"]) if err is None else []
     eng.fini()
-    out = {"first": first, "count": count, "rows": [[r[0], r[1], r[2], r[3], r[4].hex()] for r in rows],
+    out = {"first": first, "count": count, "rows": [[r[0], r[1], r[2], r[3], r[4].hex()] for r in rows], "error": err,
+           "status_names": st.as_dict()["status_names"],
            "stats": {k: v for k, v in st.as_dict().items() if isinstance(v, (int, float))}}
     gathered = [None] * world
     dist.all_gather_object(gathered, out)

@@ -66,3 +66,17 @@ def test_mixnet_multirank_vs_oracle(oracle_built, tmp_path):
     _, orows, _ = rs_trace.run_oracle("mixnet", n, sim_time=T, horizon=T, state_bytes=32, seed=42, extra=spec["margs"])
     assert rs_trace.compare(rows, orows) == []
     assert sum(g["stats"]["antimessages"] for g in got) > 0
+
+
+def test_fatal_status_on_one_rank_stops_all_ranks(oracle_built, tmp_path):
+    """A capacity overflow on ONE rank (its exchange slot: xchg_cap far too small) must end the run on EVERY rank with
+    an error, not leave the others waiting in a collective: the fatal flag travels with the per-round all-reduce and
+    the ranks that are fine report RS_ST_PEER_FATAL."""
+    rs_host.build_model("mixnet", emu=True)
+    spec = {"model": "mixnet", "n": 301, "state_bytes": 32, "margs": ["--token-prob", "0.9"], "expect_error": True,
+            "cfg": dict(master_seed=42, simulation_time=120.0, window_events=2048, arena_bytes=1024, max_payload=16, bucket_width=0.25, xchg_cap=2)}
+    rows, got = run_ranks(3, spec, tmp_path)
+    assert all(g["error"] == 6 for g in got), [g["error"] for g in got]          # RS_ERR_CAPACITY everywhere
+    names = [set(g["status_names"]) for g in got]
+    assert any("XCHG_FULL" in s for s in names)
+    assert all(("XCHG_FULL" in s) or ("PEER_FATAL" in s) for s in names)

@@ -21,7 +21,7 @@ def main():
     cfg = bench.phold_cfg(n, T)
     cfg["flags"] = rs_host.RS_F_KTIME if ktime else 0
     for k, v in over.items():
-        cfg[k] = float(v) if k == "bucket_width" else int(v)
+        cfg[k] = float(v) if k in ("bucket_width", "window_span") else int(v)
     eng = rs_host.Engine(os.environ.get("RS_LIB") or rs_host.build_model("phold"))
     if os.environ.get("RS_DEBUG"):
         eng.lib.rs_set_debug(int(os.environ["RS_DEBUG"]))
@@ -38,8 +38,6 @@ def main():
         hi = (z >> np.uint64(32)) % np.uint64(0x464FFFFE) + np.uint64(1)
         dseeds = ((hi << np.uint64(32)) | lo).astype(np.uint64)
         seeds = (C.c_uint64 * n).from_buffer(dseeds)
-        cfg["bucket_width"] = 0.0625
-        cfg["n_buckets"] = 4096
     if os.environ.get("RS_SAME_SEEDS"):
         # every LP is a twin of every other: pure same-timestamp bursts on single LPs (profiling aid)
         import ctypes as C
