@@ -30,7 +30,8 @@ enum {
 	OPT_FIRST = 128, OPT_WT, OPT_LP, OPT_OUTPUT_DIR, OPT_SCHEDULER, OPT_NPWD, OPT_P, OPT_FULL, OPT_INC, OPT_A,
 	OPT_GVT, OPT_CKTRM_MODE, OPT_GVT_SNAPSHOT_CYCLES, OPT_SIMULATION_TIME, OPT_LPS_DISTRIBUTION,
 	OPT_DETERMINISTIC_SEED, OPT_SEED, OPT_SERIAL, OPT_SEQUENTIAL, OPT_NO_CORE_BINDING, OPT_VERBOSE, OPT_STATS,
-	OPT_B_BUCKET, OPT_B_NBUCKETS, OPT_B_WINDOW, OPT_B_PENDING, OPT_B_ARENA, OPT_B_PAYLOAD, OPT_B_DEVICE, OPT_B_TRACE
+	OPT_B_BUCKET, OPT_B_NBUCKETS, OPT_B_WINDOW, OPT_B_PENDING, OPT_B_ARENA, OPT_B_PAYLOAD, OPT_B_DEVICE, OPT_B_TRACE,
+	OPT_B_SPAN, OPT_B_CHUNK, OPT_B_STEPS
 };
 
 static const struct argp_option options[] = {
@@ -63,6 +64,9 @@ static const struct argp_option options[] = {
 	{"b200-max-payload", OPT_B_PAYLOAD, "N", 0, "Largest event payload in bytes", 1},
 	{"b200-device", OPT_B_DEVICE, "N", 0, "CUDA device ordinal", 1},
 	{"b200-trace", OPT_B_TRACE, "FILE", 0, "Dump the per-LP committed-trace digest to FILE", 1},
+	{"b200-window-span", OPT_B_SPAN, "T", 0, "Widest optimistic window in simulated time", 1},
+	{"b200-chunk-events", OPT_B_CHUNK, "N", 0, "Event budget of one visit of an LP per pacing round", 1},
+	{"b200-pace-steps", OPT_B_STEPS, "N", 0, "Pacing steps per window (0 = adaptive)", 1},
 	{0}
 };
 
@@ -106,6 +110,9 @@ static error_t parse_opt(int key, char *arg, struct argp_state *state)
 	case OPT_B_PAYLOAD: cfg.max_payload = (uint32_t)strtoul(arg, NULL, 10); break;
 	case OPT_B_DEVICE: cfg.device = atoi(arg); break;
 	case OPT_B_TRACE: trace_file = arg; break;
+	case OPT_B_SPAN: cfg.window_span = atof(arg); break;
+	case OPT_B_CHUNK: cfg.chunk_events = (uint32_t)strtoul(arg, NULL, 10); break;
+	case OPT_B_STEPS: cfg.substeps = (uint32_t)strtoul(arg, NULL, 10); break;
 	case ARGP_KEY_END:
 		if (cfg.n_lps == 0)
 			argp_error(state, "Number of LPs was not provided \"--lp\"");

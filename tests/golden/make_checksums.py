@@ -7,7 +7,7 @@ exact bench configuration and stores the order-independent checksum of the per-L
 the device engine's digests in its end-to-end steps, at every GPU count, and fails on a mismatch.
 
   python tests/golden/make_checksums.py                 # 1,048,576 LPs, T=100  (~8 min, 5 GB)
-  python tests/golden/make_checksums.py 16777216 60     # 16,777,216 LPs, T=60  (~45 min, 25 GB)
+  python tests/golden/make_checksums.py 16777216 60     # 16,777,216 LPs, T=60  (~25 min, 30 GB)
 """
 import json
 import os
@@ -34,7 +34,8 @@ def main():
     with tempfile.TemporaryDirectory() as td:
         if digest is None:
             digest = os.path.join(td, "trace.txt")
-            env = dict(os.environ, RS_TRACE_OUT=digest, RS_TRACE_HORIZON=repr(T))
+            # PHOLD events carry no payload: pool the oracle's event records without payload room (16M LPs fit in memory)
+            env = dict(os.environ, RS_TRACE_OUT=digest, RS_TRACE_HORIZON=repr(T), RS_ORACLE_MAX_PAYLOAD="0")
             subprocess.run([exe, "--lp", str(n), "--seed", str(rs_trace.MASTER_SEED), "--simulation-time", repr(T)], env=env, check=True)
         cs, total = rs_trace.checksum_digest_file(digest)
     db = json.load(open(OUT)) if os.path.exists(OUT) else {}
