@@ -256,7 +256,6 @@ def test_paced_rounds(oracle_built, substeps, bw, trail, hot):
     assert st.rollbacks > 0
     if substeps > 1:
         base_rows, base = run_emu("phold", n, T, 1 << 20, arena_bytes=128, substeps=1, **({"bucket_width": bw} if bw else {}))
-        assert st.relax_rounds >= base.relax_rounds
         assert rs_trace.compare(rows, base_rows, state_mask=PHOLD_MASK) == []
 
 
