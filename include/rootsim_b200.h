@@ -87,7 +87,8 @@ typedef struct rs_config {
 	uint32_t topology_out_of;	/*   .out_of_topology                                              */
 	uint32_t hot_threshold;		/* an LP with more window events than this is a "chain LP": it gets a warp of its own
 					 * and stays one pacing step behind the others (0 = 256)                 */
-	uint32_t chain_target;		/* unused since ABI 2 (the window width no longer bounds optimism)  */
+	uint32_t run_ahead;		/* an LP whose window group starts with a burst of >= 256 same-timestamp events executes
+					 * it at once, ahead of the pacing limit: 0/1 = yes (default), 2 = no   */
 	uint32_t rank;			/* this engine's rank and the number of ranks (one engine per GPU);  */
 	uint32_t nranks;		/*   nranks <= 1 means a single engine owning every LP              */
 	uint32_t xchg_cap;		/* records per peer and exchange step (0 = 65536)                   */
@@ -121,7 +122,8 @@ typedef struct rs_stats {
 	uint32_t status;		/* RS_ST_* bits                                                    */
 	uint32_t all_lps_agree;		/* last OnGVT AND-reduction (src/gvt/ccgs.c:64-84)                 */
 	uint64_t kernel_launches;	/* engine kernels launched so far                                  */
-	uint64_t reserved[4];
+	uint64_t reserved[4];		/* diagnostics: [0] groups sorted cooperatively, [1] LPs whose own-event queue moved to a heap,
+					 * [2] run-ahead LPs (bursts executed ahead of the limit), [3] windows cut short by resource pressure */
 } rs_stats_t;
 
 /* Per-LP committed-trace digest (test/diagnostic interface; same definition as the reference-side

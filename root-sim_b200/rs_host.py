@@ -44,7 +44,7 @@ class Config(C.Structure):
         ("arena_bytes", C.c_uint32), ("max_payload", C.c_uint32), ("flags", C.c_uint32),
         ("max_pending", C.c_uint64), ("max_window", C.c_uint32), ("max_out", C.c_uint32),
         ("device", C.c_int32), ("topology_geometry", C.c_uint32), ("topology_out_of", C.c_uint32),
-        ("hot_threshold", C.c_uint32), ("chain_target", C.c_uint32), ("rank", C.c_uint32), ("nranks", C.c_uint32),
+        ("hot_threshold", C.c_uint32), ("run_ahead", C.c_uint32), ("rank", C.c_uint32), ("nranks", C.c_uint32),
         ("xchg_cap", C.c_uint32), ("chunk_events", C.c_uint32), ("substeps", C.c_uint32), ("pace_trail", C.c_uint32),
         ("window_span", C.c_double),
     ]
@@ -65,8 +65,8 @@ class Stats(C.Structure):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
         d["big_groups"] = self.reserved[0]
         d["spill_rounds"] = self.reserved[1]
-        d["redo_big"] = self.reserved[2]
-        d["redo_big_events"] = self.reserved[3]
+        d["run_ahead_lps"] = self.reserved[2]
+        d["window_cuts"] = self.reserved[3]
         d["status_names"] = [n for b, n in STATUS_BITS.items() if self.status & b]
         return d
 

@@ -221,7 +221,7 @@ def test_chunked_execution_and_checkpoint_ring(oracle_built, chunk, period):
     cases = [("mixnet", 300, 150, ["--token-prob", "0.9"], 32, dict(seed=42),
               dict(master_seed=42, window_events=2000, arena_bytes=1024, max_payload=16, bucket_width=0.25), None)]
     if rs_host.model_sources("phold") and os.path.exists(os.path.join(oracle_built, "seqp_phold")):
-        cases.append(("phold", 1024, 60, [], 8, {}, dict(master_seed=rs_trace.MASTER_SEED, window_events=1 << 20, arena_bytes=128, chain_target=64), PHOLD_MASK))
+        cases.append(("phold", 1024, 60, [], 8, {}, dict(master_seed=rs_trace.MASTER_SEED, window_events=1 << 20, arena_bytes=128, run_ahead=2), PHOLD_MASK))
         cases.append(("pcs", 64, 300, [], 56, {}, dict(master_seed=rs_trace.MASTER_SEED, window_events=256, arena_bytes=32768, max_payload=48,
                                                       bucket_width=0.25, n_buckets=4096), None))
     for model, n, T, margs, sb, okw, cfg, mask in cases:
@@ -254,6 +254,8 @@ def test_paced_rounds(oracle_built, substeps, bw, trail, hot):
     _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
     assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
     assert st.rollbacks > 0
+    if bw == 0.0 and substeps > 1:
+        assert st.as_dict()["run_ahead_lps"] > 0    # 1024 LPs per seed: same-timestamp bursts of up to 1024 events ran ahead of the limit
     if substeps > 1:
         base_rows, base = run_emu("phold", n, T, 1 << 20, arena_bytes=128, substeps=1, **({"bucket_width": bw} if bw else {}))
         assert rs_trace.compare(rows, base_rows, state_mask=PHOLD_MASK) == []
@@ -270,3 +272,31 @@ def test_wide_window_with_lagging_lps(oracle_built):
     _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
     assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
     assert st.windows <= 3 and st.rollbacks > 0 and st.relax_rounds > 32
+
+
+# ---------------------------------------------------------------- windows cut short by resource pressure
+@pytest.mark.parametrize("model,n,T,cfg,margs,sb,okw", [
+    ("phold", 4096, 60, dict(window_events=1 << 16, max_out=1 << 15, arena_bytes=128), [], 8, {}),
+    ("mixnet", 300, 150, dict(window_events=4000, max_out=6000, arena_bytes=1024, max_payload=16, bucket_width=0.25, master_seed=42),
+     ["--token-prob", "0.9"], 32, dict(seed=42)),
+])
+def test_window_cut_by_resource_pressure(oracle_built, model, n, T, cfg, margs, sb, okw):
+    """The output buffer is far too small for what a whole window sends: when it is half full the window is ended at
+    the current pacing limit (nothing at or beyond the limit has been executed or delivered; records held back beyond it
+    become future events; own events left in the LPs' queues beyond the cut are flushed to the calendar).  The committed
+    trace must not change."""
+    if model == "phold" and (not rs_host.model_sources("phold") or not os.path.exists(os.path.join(oracle_built, "seqp_phold"))):
+        pytest.skip("phold sources live in the reference tree")
+    lib = rs_host.build_model(model, emu=True)
+    kw = dict(cfg)
+    kw.setdefault("master_seed", rs_trace.MASTER_SEED)
+    with rs_host.Engine(lib, private=True) as eng:
+        eng.model_args(list(margs))
+        eng.init(n_lps=n, simulation_time=float(T), **kw)
+        assert eng.run()
+        st = eng.stats()
+        rows = rs_trace.engine_rows(eng, sb)
+    _, orows, _ = rs_trace.run_oracle(model, n, sim_time=T, horizon=T, state_bytes=sb, extra=margs, **okw)
+    assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK if model == "phold" else None) == []
+    assert st.as_dict()["window_cuts"] > 0
+    assert st.status & ~0x1 == 0
