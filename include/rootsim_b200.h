@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 2
+#define RS_ABI_VERSION 3
 
 /* error codes (reference: rootsim_error(fatal=true) -> exit(EXIT_FAILURE), src/core/core.c:220-250) */
 enum {
@@ -100,6 +100,10 @@ typedef struct rs_config {
 	uint32_t pace_trail;		/* chain LPs stay one pacing step behind: 0/1 = yes (default), 2 = no   */
 	double window_span;		/* widest optimistic window in simulated time (0 = no limit besides
 					 * window_events and 64 calendar buckets)                               */
+	uint32_t burst_events;		/* budget of one visit for events that do not advance the LP's clock (a burst of
+					 * same-timestamp events): after this many the visit stops, so that a burst does not
+					 * set the length of the rounds it is executed in (0 = chunk_events)     */
+	uint32_t reserved0;
 } rs_config_t;
 
 /* Aggregate counters; definitions follow src/statistics/statistics.h:87-103 and :345-349. */
@@ -122,6 +126,7 @@ typedef struct rs_stats {
 	uint32_t status;		/* RS_ST_* bits                                                    */
 	uint32_t all_lps_agree;		/* last OnGVT AND-reduction (src/gvt/ccgs.c:64-84)                 */
 	uint64_t kernel_launches;	/* engine kernels launched so far                                  */
+	uint64_t chain_events;		/* events executed (silent ones included) by the chain-LP kernel k_run_chain */
 	uint64_t reserved[4];		/* diagnostics: [0] groups sorted cooperatively, [1] LPs whose own-event queue moved to a heap,
 					 * [2] run-ahead LPs (bursts executed ahead of the limit), [3] windows cut short by resource pressure */
 } rs_stats_t;

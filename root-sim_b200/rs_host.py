@@ -16,7 +16,7 @@ REPO = os.path.dirname(HERE)
 BUILT = os.path.join(HERE, "_built")
 ROOTSIM_CC = os.path.join(HERE, "bin", "rootsim-cc")
 
-RS_ABI_VERSION = 2
+RS_ABI_VERSION = 3
 RS_F_TRACE = 0x1
 RS_F_KTIME = 0x2
 
@@ -46,7 +46,7 @@ class Config(C.Structure):
         ("device", C.c_int32), ("topology_geometry", C.c_uint32), ("topology_out_of", C.c_uint32),
         ("hot_threshold", C.c_uint32), ("run_ahead", C.c_uint32), ("rank", C.c_uint32), ("nranks", C.c_uint32),
         ("xchg_cap", C.c_uint32), ("chunk_events", C.c_uint32), ("substeps", C.c_uint32), ("pace_trail", C.c_uint32),
-        ("window_span", C.c_double),
+        ("window_span", C.c_double), ("burst_events", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
 
@@ -58,7 +58,7 @@ class Stats(C.Structure):
         ("late_events", C.c_uint64), ("pending_events", C.c_uint64), ("peak_window_events", C.c_uint64),
         ("gvt", C.c_double), ("loop_seconds", C.c_double), ("device_seconds", C.c_double),
         ("status", C.c_uint32), ("all_lps_agree", C.c_uint32), ("kernel_launches", C.c_uint64),
-        ("reserved", C.c_uint64 * 4),
+        ("chain_events", C.c_uint64), ("reserved", C.c_uint64 * 4),
     ]
 
     def as_dict(self):

@@ -1,6 +1,6 @@
-for args in "" "run_ahead=2" "chunk_events=1024" "chunk_events=4096" "chunk_events=1024 substeps=32"; do
-  echo "=== $args"
-  timeout 300 python tools/gpu_probe.py 1048576 100 1 $args 2>/dev/null | python -c "
+for lib in libphold_f64_4 libphold_f256_4 libphold_f64_16; do
+  echo "=== $lib"
+  RS_LIB=root-sim_b200/_built/$lib.so timeout 300 python tools/gpu_probe.py 1048576 100 1 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
