@@ -268,6 +268,11 @@ def run_ours(args):
                         "hbm_frac_whole_loop": B_ALG_PHOLD * v / 1e9 / measured_peak()[0]}
         sup = dict(best, workload="models/phold, %d LPs, T=%g, one DISTINCT seed per LP (host seed array): no twin LPs" % (n_lps, T))
 
+    # BASELINE.json configs[2] (C3): models/pcs, 65,536 cells (256 x 256 hexagons), checkpoint-bound: --p 10 and --p 1
+    pcs = None
+    if world == 1 and not args.no_pcs:
+        pcs = pcs_block(rs_host, rs_trace)
+
     parity_ok, gold = None, None
     for x in e2e_steps:
         ok, gold = check_parity(x, n_lps, T)
@@ -276,7 +281,7 @@ def run_ours(args):
     # BASELINE.json configs[3] (C4): PHOLD with 16,777,216 LPs on 2/4/8 GPUs, --simulation-time 60, one checked step
     secondary = None
     if world > 1 and not args.no_c4:
-        n4, T4 = 1 << 24, 60.0
+        n4, T4 = 1 << 24, float(args.c4_sim_time)
         cfg4 = phold_cfg(n4, T4, world)
         f4, c4 = rs_host.lp_block(lib, n4, world, rank)
         cfg4.update(device=local, rank=rank, nranks=world, lp_first=f4, lp_count=c4)
@@ -341,6 +346,8 @@ def run_ours(args):
     }
     if sup:
         line["supplementary"] = sup
+    if pcs:
+        line["pcs"] = pcs
     if secondary:
         line["secondary"] = secondary
     if rank == 0:
@@ -350,9 +357,68 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if parity_ok is False or (secondary and secondary["parity_checksum_ok"] is False):
+    if parity_ok is False or (secondary and secondary["parity_checksum_ok"] is False) or (pcs and pcs["parity_checksum_ok"] is False):
         print("bench.py: PARITY CHECKSUM MISMATCH against the oracle", file=sys.stderr)
         sys.exit(3)
+
+
+def pcs_block(rs_host, rs_trace):
+    """models/pcs (unmodified reference sources) on one GPU: 65,536 cells, --simulation-time 400, with the reference's
+    default checkpoint period (--p 10) and with a checkpoint after every event (--p 1).  Every run is checked against
+    the oracle's golden checksum (tests/golden/phold_checksums.json, key pcs_lp65536_T400).  B_alg follows SURVEY.md
+    section 8(d): E + f*E + 2*S + S/P + f*H with E = 32-byte record + 48-byte payload slot, f = records sent per
+    committed event (measured), S = measured average checkpoint size (model heap + 56-byte control block), H = 16."""
+    lib_pcs = rs_host.build_model("pcs")
+    n, T = 65536, 400.0
+    gp = os.path.join(REPO, "tests", "golden", "phold_checksums.json")
+    gold = json.load(open(gp)).get("pcs_lp%d_T%g" % (n, T)) if os.path.exists(gp) else None
+    peak = measured_peak()[0]
+    out = {"workload": "models/pcs (unmodified reference sources), %d cells, --simulation-time %g, master seed %d" % (n, T, MASTER_SEED),
+           "unit": "events/s", "parity_checksum_ok": None}
+    for p in (10, 1):
+        best = None
+        for _ in range(2):
+            eng = rs_host.Engine(lib_pcs)
+            eng.init(n_lps=n, master_seed=MASTER_SEED, simulation_time=T, window_events=1 << 20, arena_bytes=32768, max_payload=48,
+                     bucket_width=0.25, n_buckets=4096, max_pending=256 * n + (1 << 20), gvt_snapshot_cycles=1 << 30,
+                     ckpt_period=p, flags=rs_host.RS_F_TRACE)
+            fin = eng.run()
+            st = eng.stats()
+            cs, traced = rs_trace.checksum_engine(eng, 0)
+            eng.fini()
+            assert fin and (st.status & ~0x1) == 0, st.as_dict()
+            if gold is not None:
+                ok = ("%016x" % cs) == gold["checksum"] and traced == gold["traced_events_incl_init"]
+                out["parity_checksum_ok"] = ok if out["parity_checksum_ok"] is None else (out["parity_checksum_ok"] and ok)
+            committed = st.committed_events - n
+            v = committed / st.device_seconds
+            if best is None or v > best["value"]:
+                S = st.checkpoint_bytes / max(1, st.checkpoints)
+                f = st.sent_records / max(1, committed)
+                b_alg = 80.0 + f * 80.0 + 2.0 * S + S / p + f * 16.0
+                best = {"value": v, "committed_events": committed, "device_s": st.device_seconds, "windows": st.windows, "rounds": st.relax_rounds,
+                        "rollbacks": st.rollbacks, "silent_events": st.silent_events, "checkpoints": st.checkpoints,
+                        "avg_checkpoint_bytes": S, "sends_per_event": f, "algorithmic_bytes_per_event": b_alg,
+                        "hbm_frac_whole_loop": b_alg * v / 1e9 / peak, "window_cuts": st.as_dict()["window_cuts"]}
+        out["p%d" % p] = best
+    out["value"] = out["p10"]["value"]
+    exe = os.path.join(REPO, "oracle", "_ref", "pcs")
+    if os.path.exists(exe):
+        cores = max(1, min(os.cpu_count() or 1, 32))
+        with tempfile.TemporaryDirectory() as td:
+            os.makedirs(os.path.join(td, ".rootsim"))
+            open(os.path.join(td, ".rootsim", "numerical.conf"), "w").write("%d\n" % MASTER_SEED)
+            try:
+                subprocess.run([exe, "--wt", str(cores), "--lp", "1024", "--simulation-time", "400", "--deterministic-seed",
+                                "--output-dir", os.path.join(td, "o")], env=dict(os.environ, HOME=td), cwd=td, capture_output=True, text=True, timeout=300)
+                txt = open(os.path.join(td, "o", "execution_stats")).read()
+                committed = float([l for l in txt.split("\n") if l.startswith("TOTAL COMMITTED EVENTS")][0].split(":")[1])
+                secs = float([l for l in txt.split("\n") if l.startswith("TOTAL SIMULATION TIME")][0].split(":")[1].split()[0])
+                out["cpu_baseline"] = {"value": committed / secs, "unit": "events/s", "cores": cores, "kind": "reference",
+                                       "sample": "unmodified ROOT-Sim 2.0.0 (oracle/_ref/pcs) --wt %d --lp 1024 --simulation-time 400" % cores}
+            except Exception as ex:     # the baseline is a report, never a reason to lose the bench line
+                out["cpu_baseline"] = {"unavailable": str(ex)[:200]}
+    return out
 
 
 def cpu_baseline(runs):
@@ -427,6 +493,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-supplementary", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the 16M-LP secondary run of the multi-GPU bench")
+    ap.add_argument("--c4-sim-time", type=float, default=60.0, help="horizon of the 16M-LP secondary run (golden checksums exist for 30 and 60)")
+    ap.add_argument("--no-pcs", action="store_true", help="skip the models/pcs block (BASELINE configs[2]) of the 1-GPU bench")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -127,6 +127,7 @@ typedef struct rs_stats {
 	uint32_t all_lps_agree;		/* last OnGVT AND-reduction (src/gvt/ccgs.c:64-84)                 */
 	uint64_t kernel_launches;	/* engine kernels launched so far                                  */
 	uint64_t chain_events;		/* events executed (silent ones included) by the chain-LP kernel k_run_chain */
+	uint64_t sent_records;		/* records appended to the output buffer (events sent, antimessages included) */
 	uint64_t reserved[4];		/* diagnostics: [0] groups sorted cooperatively, [1] LPs whose own-event queue moved to a heap,
 					 * [2] run-ahead LPs (bursts executed ahead of the limit), [3] windows cut short by resource pressure */
 } rs_stats_t;

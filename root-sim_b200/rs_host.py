@@ -58,7 +58,7 @@ class Stats(C.Structure):
         ("late_events", C.c_uint64), ("pending_events", C.c_uint64), ("peak_window_events", C.c_uint64),
         ("gvt", C.c_double), ("loop_seconds", C.c_double), ("device_seconds", C.c_double),
         ("status", C.c_uint32), ("all_lps_agree", C.c_uint32), ("kernel_launches", C.c_uint64),
-        ("chain_events", C.c_uint64), ("reserved", C.c_uint64 * 4),
+        ("chain_events", C.c_uint64), ("sent_records", C.c_uint64), ("reserved", C.c_uint64 * 4),
     ]
 
     def as_dict(self):

@@ -8,6 +8,7 @@ the device engine's digests in its end-to-end steps, at every GPU count, and fai
 
   python tests/golden/make_checksums.py                 # 1,048,576 LPs, T=100  (~8 min, 5 GB)
   python tests/golden/make_checksums.py 16777216 60     # 16,777,216 LPs, T=60  (~25 min, 30 GB)
+  python tests/golden/make_checksums.py 65536 400 - pcs # models/pcs, 65,536 cells, T=400 (BASELINE configs[2], ~7 min)
 """
 import json
 import os
@@ -22,28 +23,31 @@ import rs_trace  # noqa: E402
 OUT = os.path.join(HERE, "phold_checksums.json")
 
 
-def key(n, T):
-    return "phold_lp%d_T%g" % (n, T)
+def key(n, T, model="phold"):
+    return "%s_lp%d_T%g" % (model, n, T)
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
     T = float(sys.argv[2]) if len(sys.argv) > 2 else 100.0
-    digest = sys.argv[3] if len(sys.argv) > 3 else None      # an existing digest file of exactly this run
-    exe = os.path.join(rs_trace.ORACLE_BUILD, "seqp_phold")
+    digest = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] != "-" else None      # an existing digest file of exactly this run
+    model = sys.argv[4] if len(sys.argv) > 4 else "phold"
+    exe = os.path.join(rs_trace.ORACLE_BUILD, "seqp_" + model)
     with tempfile.TemporaryDirectory() as td:
         if digest is None:
             digest = os.path.join(td, "trace.txt")
             # PHOLD events carry no payload: pool the oracle's event records without payload room (16M LPs fit in memory)
-            env = dict(os.environ, RS_TRACE_OUT=digest, RS_TRACE_HORIZON=repr(T), RS_ORACLE_MAX_PAYLOAD="0")
+            env = dict(os.environ, RS_TRACE_OUT=digest, RS_TRACE_HORIZON=repr(T))
+            if model == "phold":
+                env["RS_ORACLE_MAX_PAYLOAD"] = "0"
             subprocess.run([exe, "--lp", str(n), "--seed", str(rs_trace.MASTER_SEED), "--simulation-time", repr(T)], env=env, check=True)
         cs, total = rs_trace.checksum_digest_file(digest)
     db = json.load(open(OUT)) if os.path.exists(OUT) else {}
-    db[key(n, T)] = {"model": "phold", "n_lps": n, "simulation_time": T, "master_seed": rs_trace.MASTER_SEED,
-                     "oracle": "oracle/seqsim.c, rs_math.h log (seqp_phold)", "committed_events": total - n,
-                     "traced_events_incl_init": total, "checksum": "%016x" % cs}
+    db[key(n, T, model)] = {"model": model, "n_lps": n, "simulation_time": T, "master_seed": rs_trace.MASTER_SEED,
+                            "oracle": "oracle/seqsim.c, rs_math.h log (seqp_%s)" % model, "committed_events": total - n,
+                            "traced_events_incl_init": total, "checksum": "%016x" % cs}
     json.dump(db, open(OUT, "w"), indent=1, sort_keys=True)
-    print(key(n, T), db[key(n, T)])
+    print(key(n, T, model), db[key(n, T, model)])
 
 
 if __name__ == "__main__":
