@@ -103,7 +103,8 @@ typedef struct rs_config {
 	uint32_t burst_events;		/* budget of one visit for events that do not advance the LP's clock (a burst of
 					 * same-timestamp events): after this many the visit stops, so that a burst does not
 					 * set the length of the rounds it is executed in (0 = chunk_events)     */
-	uint32_t reserved0;
+	uint32_t helper_lanes;		/* the 31 idle lanes of a chain LP's warp copy, shift and scan its arrival array for it:
+					 * 0/1 = yes (default), 2 = no                                            */
 } rs_config_t;
 
 /* Aggregate counters; definitions follow src/statistics/statistics.h:87-103 and :345-349. */

@@ -46,7 +46,7 @@ class Config(C.Structure):
         ("device", C.c_int32), ("topology_geometry", C.c_uint32), ("topology_out_of", C.c_uint32),
         ("hot_threshold", C.c_uint32), ("run_ahead", C.c_uint32), ("rank", C.c_uint32), ("nranks", C.c_uint32),
         ("xchg_cap", C.c_uint32), ("chunk_events", C.c_uint32), ("substeps", C.c_uint32), ("pace_trail", C.c_uint32),
-        ("window_span", C.c_double), ("burst_events", C.c_uint32), ("reserved0", C.c_uint32),
+        ("window_span", C.c_double), ("burst_events", C.c_uint32), ("helper_lanes", C.c_uint32),
     ]
 
 
