@@ -85,19 +85,20 @@ typedef struct rs_config {
 	int32_t device;			/* CUDA device ordinal                                             */
 	uint32_t topology_geometry;	/* filled from the model's topology_settings by rs_model_info()    */
 	uint32_t topology_out_of;	/*   .out_of_topology                                              */
-	uint32_t hot_threshold;		/* an LP with more window events than this is a "chain LP": it gets a warp of its own
-					 * and stays one pacing step behind the others (0 = 256)                 */
+	uint32_t hot_threshold;		/* an LP with more window events (calendar + in-window arrivals) than this is a "chain LP":
+					 * it gets a warp of its own in k_run_chain (0 = 256)                    */
 	uint32_t run_ahead;		/* an LP whose window group starts with a burst of >= 256 same-timestamp events executes
 					 * it at once, ahead of the pacing limit: 0/1 = yes (default), 2 = no   */
 	uint32_t rank;			/* this engine's rank and the number of ranks (one engine per GPU);  */
 	uint32_t nranks;		/*   nranks <= 1 means a single engine owning every LP              */
 	uint32_t xchg_cap;		/* records per peer and exchange step (0 = 65536)                   */
 	uint32_t chunk_events;		/* event budget of one visit of an LP: after this many events it stops and goes on
-					 * in the next pacing round, while the other LPs move on (0 = 1024)      */
+					 * in the next pacing round, while the other LPs move on (0 = 1536)      */
 	uint32_t substeps;		/* pacing steps per window: the time limit below which LPs execute moves from the
 					 * window start to its end in this many rounds (0 = chosen per window so that a
 					 * step holds about one event per LP; 1 = no pacing inside a window)     */
-	uint32_t pace_trail;		/* chain LPs stay one pacing step behind: 0/1 = yes (default), 2 = no   */
+	uint32_t pace_trail;		/* chain LPs stay one pacing step behind the others: 1 = yes, 0/2 = no (default; since
+					 * arrivals are held back until the limit reaches them, trailing only costs rollbacks) */
 	double window_span;		/* widest optimistic window in simulated time (0 = no limit besides
 					 * window_events and 64 calendar buckets)                               */
 	uint32_t burst_events;		/* budget of one visit for events that do not advance the LP's clock (a burst of
