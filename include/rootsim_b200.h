@@ -57,6 +57,9 @@ enum {
 /* engine flags */
 #define RS_F_TRACE		0x1u	/* keep the per-LP committed-trace digest (count/hash/last ts)   */
 #define RS_F_KTIME		0x2u	/* time every kernel launch with CUDA events (diagnostic runs)    */
+#define RS_F_SERIAL_RUN		0x4u	/* execute a round's ordinary LPs after its chain LPs, on one stream (default: beside
+					 * them on a second stream; RS_F_KTIME implies the serial order so that its per-kernel
+					 * times add up to the step) */
 
 /*
  * Run configuration.  Mirrors the fields of the reference's `rootsim_config` that matter on this

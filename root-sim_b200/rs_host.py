@@ -19,6 +19,7 @@ ROOTSIM_CC = os.path.join(HERE, "bin", "rootsim-cc")
 RS_ABI_VERSION = 3
 RS_F_TRACE = 0x1
 RS_F_KTIME = 0x2
+RS_F_SERIAL_RUN = 0x4
 
 STATUS_BITS = {
     0x0001: "BAD_RECEIVER", 0x0002: "PAST_EVENT", 0x0004: "RESERVED_TYPE", 0x0008: "MODEL_EXIT",
