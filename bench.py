@@ -107,11 +107,13 @@ def run_ours(args):
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib_path = rs_host.build_model("phold")
+    lib_path = os.environ.get("RS_LIB") or rs_host.build_model("phold")     # (RS_LIB: a diagnostic build of the same model)
     n_lps, T = args.lps, args.sim_time
     cfg = phold_cfg(n_lps, T, world)
     cfg["device"] = local
     lib = rs_host.load(lib_path)
+    if os.environ.get("RS_DEBUG") and rank == int(os.environ.get("RS_DEBUG_RANK", "0")):
+        lib.rs_set_debug(int(os.environ["RS_DEBUG"]))       # window log on stderr (diagnostic runs only)
     first, count = rs_host.lp_block(lib, n_lps, world, rank)
     seeds = rs_host.lp_seeds(lib, MASTER_SEED, first, count)
     if world > 1:
