@@ -176,7 +176,10 @@ void rs_host_lp_seeds(uint64_t master_seed, uint32_t lp_first, uint32_t lp_count
 /* Create the device engine: allocate the LP table, state arenas, checkpoint store, calendar and
  * window buffers in HBM, copy the per-LP seeds (HOST buffer, lp_count entries; NULL = derive from
  * cfg->master_seed), and run INIT on every LP.  Replaces the parallel branch of SystemInit
- * (src/core/init.c:434-453) and initialize_worker_thread's INIT bootstrap (src/scheduler/scheduler.c:202-244). */
+ * (src/core/init.c:434-453) and initialize_worker_thread's INIT bootstrap (src/scheduler/scheduler.c:202-244).
+ * Several engines of one library may be alive at a time (each call that runs model code first claims the
+ * library's device-side engine descriptor for its engine); they must not be driven from different host threads
+ * concurrently. */
 int rs_dev_init(const rs_config_t *cfg, const uint64_t *host_seeds, rs_engine_t **out);
 
 /* Advance the simulation by at most max_windows optimistic windows (0 = until termination).

@@ -7,7 +7,7 @@
  * compile against this one unchanged.  The same file is consumed in two ways:
  *
  *   RS_DEVICE_BUILD defined   (rootsim-cc -> nvcc, sm_100a): every API entry is a __device__
- *                             function implemented in csrc/rs_device_api.cuh; the model's
+ *                             function implemented in csrc/rs_prelude.cuh; the model's
  *                             ProcessEvent/OnGVT become __device__ callbacks of the engine kernels.
  *   RS_DEVICE_BUILD undefined (plain C, gcc): ordinary external declarations.  This mode exists
  *                             for the CPU oracle under oracle/ (test infrastructure) only.

@@ -300,3 +300,32 @@ def test_window_cut_by_resource_pressure(oracle_built, model, n, T, cfg, margs, 
     assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK if model == "phold" else None) == []
     assert st.as_dict()["window_cuts"] > 0
     assert st.status & ~0x1 == 0
+
+
+def test_two_live_engines_of_one_library(oracle_built):
+    """Two engines created from ONE loaded library and run in alternation (a few windows each): the model API reaches
+    the engine through one per-library descriptor, which every rs_dev_run claims for its own engine first
+    (a second live engine silently redirected the first one's sends)."""
+    if not rs_host.model_sources("phold") or not os.path.exists(os.path.join(oracle_built, "seqp_phold")):
+        pytest.skip("phold sources live in the reference tree")
+    lib = rs_host.build_model("phold", emu=True)
+    a, b = rs_host.Engine(lib), rs_host.Engine(lib)
+    assert a.lib is b.lib or a.lib._handle == b.lib._handle
+    a.init(n_lps=96, master_seed=rs_trace.MASTER_SEED, simulation_time=60.0, window_events=200, arena_bytes=128)
+    b.init(n_lps=200, master_seed=rs_trace.MASTER_SEED, simulation_time=40.0, window_events=300, arena_bytes=128)
+    fa = fb = False
+    for _ in range(10000):
+        if not fa:
+            fa = a.run(max_windows=2)
+        if not fb:
+            fb = b.run(max_windows=3)
+        if fa and fb:
+            break
+    assert fa and fb
+    for eng, n, T in ((a, 96, 60), (b, 200, 40)):
+        rows = rs_trace.engine_rows(eng, 8)
+        _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+        assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
+        assert eng.stats().status & ~0x1 == 0
+    a.fini()
+    b.fini()

@@ -209,3 +209,28 @@ def test_event_latency_probe(oracle_built):
         eng.init(n_lps=1024, master_seed=1, simulation_time=10.0, max_out=1 << 18)
         ns = eng.probe_event(5, 3, 2000, True)
         assert 50.0 < ns < 20000.0
+
+
+def test_two_live_engines_of_one_library(oracle_built):
+    """Two device engines from ONE loaded library, run in alternation a few windows at a time: every rs_dev_run claims
+    the library's __constant__ engine descriptor for its own engine before it launches model code."""
+    need("phold", oracle_built)
+    lib = rs_host.build_model("phold")
+    a, b = rs_host.Engine(lib), rs_host.Engine(lib)
+    a.init(n_lps=4096, master_seed=rs_trace.MASTER_SEED, simulation_time=40.0, window_events=8192, arena_bytes=128)
+    b.init(n_lps=1000, master_seed=rs_trace.MASTER_SEED, simulation_time=60.0, window_events=4096, arena_bytes=128)
+    fa = fb = False
+    for _ in range(10000):
+        if not fa:
+            fa = a.run(max_windows=1)
+        if not fb:
+            fb = b.run(max_windows=2)
+        if fa and fb:
+            break
+    assert fa and fb
+    for eng, n, T in ((a, 4096, 40), (b, 1000, 60)):
+        rows = rs_trace.engine_rows(eng, 8)
+        _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+        assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
+    a.fini()
+    b.fini()
