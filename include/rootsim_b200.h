@@ -44,7 +44,8 @@ enum {
 #define RS_ST_POOL_FULL		0x0020u	/* pending-event pool exhausted                                 */
 #define RS_ST_WINDOW_FULL	0x0040u	/* window/grouping buffer exhausted                             */
 #define RS_ST_OUT_FULL		0x0080u	/* per-window output (sent-log) buffer exhausted                */
-#define RS_ST_HORIZON		0x0100u	/* event beyond the calendar horizon (n_buckets*bucket_width)   */
+#define RS_ST_HORIZON		0x0100u	/* far list full: too many events beyond the calendar ring's horizon
+					 * (n_buckets*bucket_width); such events normally wait on the far list */
 #define RS_ST_LATE_FULL		0x0200u	/* too many in-window arrivals for one LP                       */
 #define RS_ST_PAYLOAD		0x0400u	/* event payload larger than max_payload                        */
 #define RS_ST_NO_EVENTS		0x0800u	/* pending set became empty before the horizon                  */

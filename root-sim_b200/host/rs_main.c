@@ -10,7 +10,8 @@
  * options are chained as an argp child exactly like the reference does (src/core/init.c:385-390,419).
  * Extra `--b200-*` options size the device pools.
  *
- * Output: <output-dir>/execution_stats with the labels of src/statistics/statistics.c:345-394 and the
+ * Output: <output-dir>/execution_stats, thread_0_0/local_stats, thread_0_0/lps (--stats all|lp) with the labels of
+ * src/statistics/statistics.c:345-394,483-505 and the
  * final "SIMULATION CORRECTLY COMPLETED" banner (:396-405); TIME BARRIER lines like src/main.c:150-165.
  */
 #define _GNU_SOURCE
@@ -74,6 +75,7 @@ static rs_config_t cfg;
 static const char *output_dir = "outputs";
 static const char *trace_file;
 static bool deterministic_seed, seed_given, verbose;
+static bool stats_lp = true;	/* --stats all (the reference's default) or lp: per-LP rows in thread_0_0/lps */
 
 static error_t parse_opt(int key, char *arg, struct argp_state *state)
 {
@@ -99,8 +101,11 @@ static error_t parse_opt(int key, char *arg, struct argp_state *state)
 		argp_error(state, "--sequential is not available: this runtime is the optimistic B200 engine");
 		break;
 	case OPT_VERBOSE: verbose = true; break;
+	case OPT_STATS:		/* src/core/init.c:213-215: all | performance | lp | global */
+		stats_lp = (!strcmp(arg, "all") || !strcmp(arg, "lp"));
+		break;
 	case OPT_WT: case OPT_SCHEDULER: case OPT_FULL: case OPT_GVT: case OPT_CKTRM_MODE: case OPT_LPS_DISTRIBUTION:
-	case OPT_NO_CORE_BINDING: case OPT_STATS:
+	case OPT_NO_CORE_BINDING:
 		break;
 	case OPT_B_BUCKET: cfg.bucket_width = atof(arg); break;
 	case OPT_B_NBUCKETS: cfg.n_buckets = (uint32_t)strtoul(arg, NULL, 10); break;
@@ -248,21 +253,35 @@ int main(int argc, char **argv)
 		fclose(fg);
 	}
 	free(gvt_rows);
-	snprintf(path, sizeof path, "%s/execution_stats", output_dir);
-	FILE *f = fopen(path, "w");
-	if (f) {
+	/* <output-dir>/execution_stats (node statistics) and <output-dir>/thread_0_0/local_stats (the statistics of the one
+	 * "worker thread" there is: the device), labels of print_common_stats (src/statistics/statistics.c:345-394) */
+	for (int which = 0; which < 2; which++) {
+		snprintf(path, sizeof path, which ? "%s/thread_0_0/local_stats" : "%s/execution_stats", output_dir);
+		FILE *f = fopen(path, "w");
+		if (!f)
+			continue;
 		double tot = (double)st.executed_events + (double)st.silent_events;
 		double rb_freq = tot > 0 ? (double)st.rollbacks / tot : 0;
 		double rb_len = st.rollbacks ? (tot - (double)st.committed_events) / (double)st.rollbacks : 0;
 		fprintf(f, "------------------------------------------------------------\n");
-		fprintf(f, "-------------------- GLOBAL STATISTICS ---------------------\n");
+		fprintf(f, "-------------------- %s ---------------------\n", which ? "THREAD STATISTICS" : "GLOBAL STATISTICS");
 		fprintf(f, "------------------------------------------------------------\n\n");
-		fprintf(f, "SIMULATION STARTED AT ..... : %s \n", t_start);
-		fprintf(f, "SIMULATION FINISHED AT .... : %s \n", t_end);
-		fprintf(f, "TOTAL SIMULATION TIME ..... : %.03f seconds \n\n", st.loop_seconds);
+		if (!which) {
+			fprintf(f, "SIMULATION STARTED AT ..... : %s \n", t_start);
+			fprintf(f, "SIMULATION FINISHED AT .... : %s \n", t_end);
+			fprintf(f, "TOTAL SIMULATION TIME ..... : %.03f seconds \n\n", st.loop_seconds);
+		}
 		fprintf(f, "TOTAL KERNELS ............. : %d \n", 1);
-		fprintf(f, "TOTAL_THREADS ............. : %d \n", 1);
-		fprintf(f, "TOTAL LPs.................. : %u \n\n", cfg.n_lps);
+		if (which) {
+			fprintf(f, "KERNEL ID ................. : %d \n", 0);
+			fprintf(f, "LPs HOSTED BY KERNEL....... : %u \n", cfg.n_lps);
+			fprintf(f, "TOTAL_THREADS ............. : %d \n", 1);
+			fprintf(f, "THREAD ID ................. : %d \n", 0);
+			fprintf(f, "LPs HOSTED BY THREAD ...... : %u \n\n", cfg.n_lps);
+		} else {
+			fprintf(f, "TOTAL_THREADS ............. : %d \n", 1);
+			fprintf(f, "TOTAL LPs.................. : %u \n\n", cfg.n_lps);
+		}
 		fprintf(f, "TOTAL EXECUTED EVENTS ..... : %.0f \n", tot);
 		fprintf(f, "TOTAL COMMITTED EVENTS..... : %llu \n", (unsigned long long)st.committed_events);
 		fprintf(f, "TOTAL REPROCESSED EVENTS... : %llu \n", (unsigned long long)st.silent_events);
@@ -273,7 +292,8 @@ int main(int argc, char **argv)
 		fprintf(f, "EFFICIENCY................. : %.2f %%\n", (1 - rb_freq * rb_len) * 100);
 		fprintf(f, "AVERAGE EVENT COST......... : %.4f us\n", tot > 0 ? st.device_seconds * 1e6 / tot : 0);
 		fprintf(f, "AVERAGE LOG SIZE........... : %.2f B\n", st.checkpoints ? (double)st.checkpoint_bytes / (double)st.checkpoints : 0);
-		fprintf(f, "\nLAST COMMITTED GVT ........ : %f\n", st.gvt);
+		if (!which)
+			fprintf(f, "\nLAST COMMITTED GVT ........ : %f\n", st.gvt);
 		fprintf(f, "NUMBER OF GVT REDUCTIONS... : %llu\n", (unsigned long long)st.windows);
 		fprintf(f, "SIMULATION TIME SPEED...... : %.2f units per GVT\n", st.windows ? st.gvt / (double)st.windows : 0);
 		fprintf(f, "IN-WINDOW DELIVERIES....... : %llu\n", (unsigned long long)st.late_events);
@@ -282,6 +302,25 @@ int main(int argc, char **argv)
 		fprintf(f, "DEVICE STATUS BITS......... : 0x%x\n", st.status);
 		fprintf(f, "\n--------- SIMULATION %s ----------\n", rc == RS_OK ? "CORRECTLY COMPLETED" : "ABNORMALLY TERMINATED");
 		fclose(f);
+	}
+	if (stats_lp) {
+		/* <output-dir>/thread_0_0/lps: one row per LP, header and columns of src/statistics/statistics.c:483-505.  The
+		 * engine keeps the committed event count per LP; executed/rolled-back counts, rollbacks and antimessages exist as
+		 * totals only (execution_stats), so those columns repeat the committed count or are 0. */
+		rs_lp_trace_t *lt = malloc(sizeof(rs_lp_trace_t) * cfg.n_lps);
+		snprintf(path, sizeof path, "%s/thread_0_0/lps", output_dir);
+		FILE *fl = lt ? fopen(path, "w") : NULL;
+		if (fl && rs_dev_trace(eng, lt, cfg.n_lps) == RS_OK) {
+			fprintf(fl, "#%15.15s   %15.15s   %15.15s   %15.15s", "\"GID\"", "\"LID\"", "\"TOTAL EVENTS\"", "\"COMM EVENTS\"");
+			fprintf(fl, "   %15.15s   %15.15s   %15.15s   %15.15s", "\"REPROC EVENTS\"", "\"ROLLBACKS\"", "\"ANTIMSG\"", "\"AVG EVT COST\"");
+			fprintf(fl, "   %15.15s   %15.15s   %15.15s\n", "\"AVG CKPT COST\"", "\"AVG REC COST\"", "\"IDLE CYCLES\"");
+			for (uint32_t i = 0; i < cfg.n_lps; i++)
+				fprintf(fl, " %15u   %15u   %15.0lf   %15.0lf   %15.0lf   %15.0lf   %15.0lf   %15lf   %15.0lf   %15.0lf   %15.0lf   \n",
+					i, i, (double)lt[i].count, (double)lt[i].count, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0);
+		}
+		if (fl)
+			fclose(fl);
+		free(lt);
 	}
 	if (trace_file) {
 		rs_lp_trace_t *tr = malloc(sizeof(rs_lp_trace_t) * cfg.n_lps);

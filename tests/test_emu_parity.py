@@ -203,9 +203,14 @@ def test_cli_executable_emu(oracle_built, tmp_path):
     stats = open(out / "execution_stats").read()
     for label in ("TOTAL EXECUTED EVENTS", "TOTAL COMMITTED EVENTS", "TOTAL ROLLBACKS EXECUTED", "TOTAL ANTIMESSAGES", "EFFICIENCY", "LAST COMMITTED GVT"):
         assert label in stats
+    local = open(out / "thread_0_0" / "local_stats").read()                # statistics.c:518-521
+    assert "THREAD STATISTICS" in local and "LPs HOSTED BY THREAD ...... : 200" in local and "TOTAL COMMITTED EVENTS" in local
     _, rows = rs_trace.parse_digest(str(tr))
     _, orows, _ = rs_trace.run_oracle("mixnet", 200, sim_time=60, horizon=60, seed=42, extra=["--mean", "3.0"])
     assert rs_trace.compare(rows, orows) == []
+    lps = [l.split() for l in open(out / "thread_0_0" / "lps").read().split("\n") if l.strip() and not l.startswith("#")]   # statistics.c:483-505
+    assert len(lps) == 200 and all(len(r) == 11 for r in lps)
+    assert [int(r[3]) for r in lps] == [r[0] for r in orows]              # committed events per LP
     # the sequential engine is the reference's own: asking this runtime for it is an error, like an unknown option
     r = subprocess.run([str(exe), "--lp", "8", "--sequential"], capture_output=True, text=True)
     assert r.returncode != 0
@@ -329,3 +334,26 @@ def test_two_live_engines_of_one_library(oracle_built):
         assert eng.stats().status & ~0x1 == 0
     a.fini()
     b.fini()
+
+
+@pytest.mark.parametrize("model,n,T,nb,bw,margs", [
+    ("phold", 257, 80, 64, 0.0625, []),          # ring = 4 time units, mean increment 5: most events start on the far list
+    ("phold", 1024, 40, 128, 0.03125, []),
+    ("mixnet", 200, 120, 64, 0.25, ["--mean", "30.0"]),     # payloads travel through the far list too
+])
+def test_far_future_events_wait_on_the_far_list(oracle_built, model, n, T, nb, bw, margs):
+    """An event beyond the calendar ring's horizon (n_buckets x bucket_width) is not an error: it waits on the far
+    list and is re-filed when the ring has advanced (the reference's list_insert takes any timestamp,
+    src/datatypes/list.h:163-208)."""
+    if model == "phold" and (not rs_host.model_sources("phold") or not os.path.exists(os.path.join(oracle_built, "seqp_phold"))):
+        pytest.skip("phold sources live in the reference tree")
+    if model == "phold":
+        rows, st = run_emu("phold", n, T, 4096, arena_bytes=128, n_buckets=nb, bucket_width=bw)
+        _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+        assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
+    else:
+        rows, st = run_emu("mixnet", n, T, 4096, margs, state_bytes=32, seed=42, arena_bytes=1024, max_payload=16, n_buckets=nb, bucket_width=bw)
+        _, orows, _ = rs_trace.run_oracle("mixnet", n, sim_time=T, horizon=T, state_bytes=32, seed=42, extra=margs)
+        assert rs_trace.compare(rows, orows) == []
+    assert st.status & ~0x1 == 0
+    assert st.committed_events == sum(r[0] for r in orows)

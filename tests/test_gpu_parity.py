@@ -234,3 +234,14 @@ def test_two_live_engines_of_one_library(oracle_built):
         assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
     a.fini()
     b.fini()
+
+
+@pytest.mark.parametrize("n,T,nb,bw", [(4096, 40, 64, 0.0625), (65536, 20, 128, 0.03125)])
+def test_far_future_events_wait_on_the_far_list(oracle_built, n, T, nb, bw):
+    """calendar ring of 4 time units: most PHOLD events (mean increment 5) are committed beyond the ring's horizon,
+    wait on the far list and are re-filed when the ring has advanced (src/datatypes/list.h:163-208 takes any timestamp)"""
+    need("phold", oracle_built)
+    rows, st = run_gpu("phold", n, T, window_events=1 << 20, arena_bytes=128, n_buckets=nb, bucket_width=bw)
+    _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+    assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
+    assert st.status & ~0x1 == 0

@@ -56,6 +56,22 @@ def test_phold_multirank_vs_oracle(oracle_built, tmp_path, world, n, T):
     assert len({g["stats"]["windows"] for g in got}) == 1          # lock step: same number of windows everywhere
 
 
+def test_phold_multirank_far_list(oracle_built, tmp_path):
+    """a calendar ring of 4 time units on every rank: most events (mean increment 5) wait on the ranks' far lists and
+    the agreed first bucket must take them into account"""
+    if not rs_host.model_sources("phold") or not os.path.exists(os.path.join(oracle_built, "seqp_phold")):
+        pytest.skip("phold sources live in the reference tree")
+    rs_host.build_model("phold", emu=True)
+    n, T = 700, 50
+    spec = {"model": "phold", "n": n, "state_bytes": 8,
+            "cfg": dict(master_seed=rs_trace.MASTER_SEED, simulation_time=float(T), window_events=4096, arena_bytes=128,
+                        n_buckets=64, bucket_width=0.0625)}
+    rows, got = run_ranks(3, spec, tmp_path)
+    _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+    assert rs_trace.compare(rows, orows, state_mask=[0, 4, 5, 6, 7]) == []
+    assert sum(g["stats"]["committed_events"] for g in got) == sum(r[0] for r in orows)
+
+
 def test_mixnet_multirank_vs_oracle(oracle_built, tmp_path):
     """payloads, zero-delay events across ranks (antimessages travel between ranks), model heap"""
     rs_host.build_model("mixnet", emu=True)
