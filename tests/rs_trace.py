@@ -148,12 +148,16 @@ def checksum_rows(rows, first_gid=0):
     return checksum_arrays([r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows], [r[3] for r in rows], first_gid)
 
 
-def checksum_engine(eng, first_gid=0):
-    """checksum of a device engine's per-LP digests (one D2H copy of 32 bytes per LP through rs_dev_trace)"""
+def checksum_digests(tr, first_gid=0):
+    """checksum of the per-LP digest array rs_dev_trace returned (32 bytes per LP)"""
     import numpy as np
-    tr = eng.trace()
     a = np.frombuffer(tr, dtype=np.dtype([("count", "<u8"), ("hash", "<u8"), ("ts", "<u8"), ("seed", "<u8")]))
     return checksum_arrays(a["count"], a["hash"], a["ts"], a["seed"], first_gid)
+
+
+def checksum_engine(eng, first_gid=0):
+    """checksum of a device engine's per-LP digests (one D2H copy of 32 bytes per LP through rs_dev_trace)"""
+    return checksum_digests(eng.trace(), first_gid)
 
 
 def checksum_digest_file(path):
