@@ -245,3 +245,17 @@ def test_far_future_events_wait_on_the_far_list(oracle_built, n, T, nb, bw):
     _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
     assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
     assert st.status & ~0x1 == 0
+
+
+@pytest.mark.parametrize("cfg", [dict(flags=rs_host.RS_F_TRACE | rs_host.RS_F_SERIAL_RUN), dict(helper_lanes=2), dict(flags=rs_host.RS_F_TRACE | rs_host.RS_F_KTIME, helper_lanes=2),
+                                 dict(hot_threshold=8), dict(chunk_events=64)])
+def test_execution_modes_commit_the_same_trace(oracle_built, cfg):
+    """The scheduling choices of the engine -- ordinary LPs beside or after the chain LPs (two streams / one), arrival
+    merge by the helper lanes or by lane 0 alone, which LPs get a warp of their own, the visit budget -- change how the
+    work is laid out on the GPU, never the committed trace."""
+    need("phold", oracle_built)
+    n, T = 65536, 25
+    rows, st = run_gpu("phold", n, T, window_events=1 << 20, arena_bytes=128, **cfg)
+    _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+    assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
+    assert st.status & ~0x1 == 0
