@@ -276,6 +276,14 @@ def run_ours(args):
     if world == 1 and not args.no_pcs:
         pcs = pcs_block(rs_host, rs_trace)
 
+    # SURVEY.md section 8(f) rank 3 (BASELINE config 5): models/traffic on a generated road grid
+    traffic = None
+    if world == 1 and not args.no_traffic:
+        try:
+            traffic = traffic_block(rs_host, rs_trace)
+        except Exception as ex:         # a widened row never costs the headline line
+            traffic = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:300]), "parity_checksum_ok": None}
+
     parity_ok, gold = None, None
     for x in e2e_steps:
         ok, gold = check_parity(x, n_lps, T)
@@ -351,6 +359,8 @@ def run_ours(args):
         line["supplementary"] = sup
     if pcs:
         line["pcs"] = pcs
+    if traffic:
+        line["traffic"] = traffic
     if secondary:
         line["secondary"] = secondary
     if rank == 0:
@@ -360,7 +370,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if parity_ok is False or (secondary and secondary["parity_checksum_ok"] is False) or (pcs and pcs["parity_checksum_ok"] is False):
+    if parity_ok is False or (secondary and secondary["parity_checksum_ok"] is False) or (pcs and pcs["parity_checksum_ok"] is False) \
+            or (traffic and traffic["parity_checksum_ok"] is False):
         print("bench.py: PARITY CHECKSUM MISMATCH against the oracle", file=sys.stderr)
         sys.exit(3)
 
@@ -419,6 +430,71 @@ def pcs_block(rs_host, rs_trace):
                 secs = float([l for l in txt.split("\n") if l.startswith("TOTAL SIMULATION TIME")][0].split(":")[1].split()[0])
                 out["cpu_baseline"] = {"value": committed / secs, "unit": "events/s", "cores": cores, "kind": "reference",
                                        "sample": "unmodified ROOT-Sim 2.0.0 (oracle/_ref/pcs) --wt %d --lp 1024 --simulation-time 400" % cores}
+            except Exception as ex:     # the baseline is a report, never a reason to lose the bench line
+                out["cpu_baseline"] = {"unavailable": str(ex)[:200]}
+    return out
+
+
+def traffic_block(rs_host, rs_trace):
+    """models/traffic (unmodified reference sources) on one GPU: the generated 16 x 16 road grid (256 junctions + 3840
+    road segments = 4096 LPs, tests/golden/make_traffic_topology.py), one simulated hour.  INIT runs on the device and
+    parses the topology image the host loaded.  Checked against the oracle's golden checksum (key traffic_lp4096_T3600);
+    the unmodified reference with all host threads runs beside it.  The run is bounded by the event chain of the
+    busiest junction (cars enter at junctions only), not by bandwidth: 4096 LPs cannot fill 148 SMs."""
+    sys.path.insert(0, os.path.join(REPO, "tests", "golden"))
+    import make_traffic_topology as mt
+    name, T = "traffic_grid_lp4096", 3600.0
+    text, n = mt.topology(name)
+    lib = rs_host.build_model("traffic")
+    gp = os.path.join(REPO, "tests", "golden", "phold_checksums.json")
+    gold = json.load(open(gp)).get("traffic_lp%d_T%g" % (n, T)) if os.path.exists(gp) else None
+    out = {"workload": "models/traffic (unmodified reference sources), generated road grid %s (%d LPs), --simulation-time %g, master seed %d"
+                       % (name, n, T, MASTER_SEED), "unit": "events/s", "parity_checksum_ok": None}
+    best = None
+    for _ in range(2):
+        eng = rs_host.Engine(lib)
+        eng.model_file("topology.txt", text.encode())
+        t0 = time.time()
+        eng.init(n_lps=n, master_seed=MASTER_SEED, simulation_time=T, window_events=1 << 18, arena_bytes=1 << 17, max_payload=16,
+                 bucket_width=4.0, n_buckets=4096, flags=rs_host.RS_F_TRACE)
+        t_init = time.time() - t0
+        fin = False
+        while not fin and time.time() - t0 < 120.0:      # bounded: this block must never hold up the bench
+            fin = eng.run(max_windows=2)
+        st = eng.stats()
+        cs, traced = rs_trace.checksum_engine(eng, 0)
+        eng.fini()
+        if not fin:
+            out["unfinished"] = "not finished after 120 s (gvt %g of %g)" % (st.gvt, T)
+            break
+        assert (st.status & ~0x1) == 0, st.as_dict()
+        if gold is not None:
+            ok = ("%016x" % cs) == gold["checksum"] and traced == gold["traced_events_incl_init"]
+            out["parity_checksum_ok"] = ok if out["parity_checksum_ok"] is None else (out["parity_checksum_ok"] and ok)
+        committed = st.committed_events - n
+        v = committed / st.device_seconds
+        if best is None or v > best["value"]:
+            best = {"value": v, "committed_events": committed, "device_s": st.device_seconds, "init_s_incl_file_parse_on_device": t_init,
+                    "e2e_value": committed / (time.time() - t0), "windows": st.windows, "rounds": st.relax_rounds,
+                    "rollbacks": st.rollbacks, "silent_events": st.silent_events, "checkpoints": st.checkpoints,
+                    "avg_checkpoint_bytes": st.checkpoint_bytes / max(1, st.checkpoints), "kernel_launches": st.kernel_launches}
+    if best:
+        out.update(best)
+    exe = os.path.join(REPO, "oracle", "_ref", "traffic")
+    if os.path.exists(exe):
+        cores = max(1, min(os.cpu_count() or 1, 32))
+        with tempfile.TemporaryDirectory() as td:
+            os.makedirs(os.path.join(td, ".rootsim"))
+            open(os.path.join(td, ".rootsim", "numerical.conf"), "w").write("%d\n" % MASTER_SEED)
+            open(os.path.join(td, "topology.txt"), "w").write(text)
+            try:
+                subprocess.run([exe, "--wt", str(cores), "--lp", str(n), "--simulation-time", "%d" % T, "--deterministic-seed",
+                                "--output-dir", os.path.join(td, "o")], env=dict(os.environ, HOME=td), cwd=td, capture_output=True, text=True, timeout=300)
+                txt = open(os.path.join(td, "o", "execution_stats")).read()
+                committed = float([l for l in txt.split("\n") if l.startswith("TOTAL COMMITTED EVENTS")][0].split(":")[1])
+                secs = float([l for l in txt.split("\n") if l.startswith("TOTAL SIMULATION TIME")][0].split(":")[1].split()[0])
+                out["cpu_baseline"] = {"value": committed / secs, "unit": "events/s", "cores": cores, "kind": "reference",
+                                       "sample": "unmodified ROOT-Sim 2.0.0 (oracle/_ref/traffic) --wt %d --lp %d --simulation-time %d, same topology" % (cores, n, T)}
             except Exception as ex:     # the baseline is a report, never a reason to lose the bench line
                 out["cpu_baseline"] = {"unavailable": str(ex)[:200]}
     return out
@@ -497,6 +573,7 @@ def main():
     ap.add_argument("--no-supplementary", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the 16M-LP secondary run of the multi-GPU bench")
     ap.add_argument("--c4-sim-time", type=float, default=60.0, help="horizon of the 16M-LP secondary run (golden checksums exist for 30 and 60)")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the models/traffic block (SURVEY 8(f) rank 3) of the 1-GPU bench")
     ap.add_argument("--no-pcs", action="store_true", help="skip the models/pcs block (BASELINE configs[2]) of the 1-GPU bench")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -167,6 +167,16 @@ void rs_model_info(rs_model_info_t *out);
  * go through host/rs_main.c).  argv[0] is skipped, like main()'s.  Returns 0 on success. */
 int rs_model_args(int argc, char **argv);
 
+/* Input files of the model.  The reference runs INIT on a CPU thread, so a model may fopen() a file there
+ * (models/traffic/init.c:280-313 parses topology.txt once per LP).  Here INIT runs on the device: rs_dev_init
+ * loads every file the model opens for reading under a literal name (found by rootsim-cc) from the working
+ * directory -- where the reference's fopen would look; a missing file fails rs_dev_init with RS_ERR_MODEL, as
+ * the model's own check would -- and the model's unchanged parsing code reads the image (fopen/fgets/rewind/
+ * fclose/strtok_r/strtod ... of csrc/rs_prelude.cuh).  rs_model_file hands over the bytes of a file from HOST
+ * memory instead (copied; data == NULL forgets the name); it must be called before rs_dev_init and takes
+ * precedence over the working directory. */
+int rs_model_file(const char *name, const void *data, size_t len);
+
 /* Fill cfg with the defaults of the reference CLI (src/core/init.c:315-340) and of the engine. */
 void rs_config_defaults(rs_config_t *cfg);
 

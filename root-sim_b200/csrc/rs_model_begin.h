@@ -20,3 +20,27 @@
  * statement is dropped, the function keeps its C fallthrough behaviour. */
 #define __asm__
 #define __volatile__(...)
+/* libc of a model whose INIT parses an input file (models/traffic/init.c): in-memory stdio over the images the
+ * host loaded (rs_prelude.cuh), string functions with device bodies */
+#define FILE			rs_FILE
+#define fopen(p, m)		rs_fopen((p), (m))
+#define fclose(f)		rs_fclose(f)
+#define fgets(b, n, f)		rs_fgets((b), (n), (f))
+#define fgetc(f)		rs_fgetc(f)
+#define feof(f)			rs_feof(f)
+#define rewind(f)		rs_rewind(f)
+#define perror(s)		rs_perror(s)
+#define strlen(s)		rs_strlen(s)
+#define strcmp(a, b)		rs_strcmp((a), (b))
+#define strncmp(a, b, n)	rs_strncmp((a), (b), (n))
+#define strcpy(d, s)		rs_strcpy((d), (s))
+#define strncpy(d, s, n)	rs_strncpy((d), (s), (n))
+#define strtok_r(s, d, p)	rs_strtok_r((s), (d), (p))
+#define strtod(s, e)		rs_strtod((s), (e))
+#define atoi(s)			rs_atoi(s)
+/* C semantics of abs(): the argument is converted to int (models/traffic/functions.c:125 relies on it) */
+#define abs(x)			rs_c_abs((int)(x))
+/* log/exp steer timestamps and coin tosses: the portable versions give the same bits on the device, in the
+ * emulation and in the CPU oracle (rs_math.h) */
+#define log(x)			rs_log(x)
+#define exp(x)			rs_exp(x)

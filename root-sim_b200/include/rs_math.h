@@ -81,3 +81,60 @@ RS_HD double rs_log(double x)
 	const double hfsq = 0.5 * f * f;
 	return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
 }
+
+/*
+ * rs_exp: x = k*ln2 + r with |r| <= ln2/2 (r kept as hi - lo), exp(r) = 1 + r + r*c/(2 - c) with
+ * c = r - r^2 * P(r^2), P a degree-5 minimax polynomial (reduction and coefficients: fdlibm e_exp.c),
+ * result scaled by 2^k with exact power-of-two multiplications.  Used where a model calls exp() and the
+ * result steers the trace (models/traffic/normal_cdf.c:62,76: the accident probability that a coin is
+ * compared with); <= 1 ULP of glibc exp over the tested range (tests/test_rs_math.py).
+ */
+RS_HD double rs_exp(double x)
+{
+	const double ln2_hi = 6.93147180369123816490e-01;	/* 0x3fe62e42fee00000 */
+	const double ln2_lo = 1.90821492927058770002e-10;	/* 0x3dea39ef35793c76 */
+	const double inv_ln2 = 1.44269504088896338700e+00;
+	const double P1 = 1.66666666666666019037e-01;
+	const double P2 = -2.77777777770155933842e-03;
+	const double P3 = 6.61375632143793436117e-05;
+	const double P4 = -1.65339022054652515390e-06;
+	const double P5 = 4.13813679705723846039e-08;
+
+	const uint64_t ux = rs_d2u(x);
+	const uint64_t ax = ux & 0x7fffffffffffffffULL;
+	const int neg = (int)(ux >> 63);
+	if (ax > 0x7ff0000000000000ULL)
+		return x + x;						/* NaN */
+	if (x > 7.09782712893383973096e+02)
+		return rs_u2d(0x7ff0000000000000ULL);			/* overflow */
+	if (x < -7.45133219101941108420e+02)
+		return 0.0;						/* underflow */
+	double hi = 0.0, lo = 0.0;
+	int k = 0;
+	if (ax > 0x3fd62e42fefa39efULL) {				/* |x| > ln2/2 */
+		if (ax < 0x3ff0a2b23f3bab73ULL) {			/* |x| < 3 ln2/2 */
+			hi = neg ? x + ln2_hi : x - ln2_hi;
+			lo = neg ? -ln2_lo : ln2_lo;
+			k = neg ? -1 : 1;
+		} else {
+			k = (int)(inv_ln2 * x + (neg ? -0.5 : 0.5));
+			const double t = (double)k;
+			hi = x - t * ln2_hi;
+			lo = t * ln2_lo;
+		}
+		x = hi - lo;
+	} else if (ax < 0x3e30000000000000ULL) {			/* |x| < 2^-28 */
+		return 1.0 + x;
+	}
+	const double t = x * x;
+	const double c = x - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+	if (k == 0)
+		return 1.0 - ((x * c) / (c - 2.0) - x);
+	double y = 1.0 - ((lo - (x * c) / (2.0 - c)) - hi);
+	if (k >= -1021) {
+		if (k == 1024)
+			return y * 2.0 * rs_u2d(0x7fe0000000000000ULL);
+		return y * rs_u2d((uint64_t)(1023 + k) << 52);
+	}
+	return y * rs_u2d((uint64_t)(1023 + k + 1000) << 52) * rs_u2d((uint64_t)(1023 - 1000) << 52);
+}

@@ -97,7 +97,7 @@ class ModelInfo(C.Structure):
 EXPORTS = ["rs_model_args", "rs_model_info", "rs_config_defaults", "rs_host_lp_seeds", "rs_dev_init", "rs_dev_run", "rs_dev_stats",
            "rs_dev_trace", "rs_dev_lp_state", "rs_dev_set_comm", "rs_nccl_unique_id", "rs_dev_comm_init_nccl", "rs_nccl_comm_create", "rs_dev_set_nccl_comm",
            "rs_nccl_comm_destroy", "rs_host_lp_block",
-           "rs_dev_kernel_times", "rs_dev_probe_event", "rs_dev_ipc_export", "rs_dev_ipc_import", "rs_set_debug", "rs_dev_error", "rs_dev_fini"]
+           "rs_dev_kernel_times", "rs_dev_probe_event", "rs_dev_ipc_export", "rs_dev_ipc_import", "rs_set_debug", "rs_dev_error", "rs_dev_fini", "rs_model_file"]
 
 
 def load(path):
@@ -106,6 +106,8 @@ def load(path):
     lib.rs_model_info.restype = None
     lib.rs_model_args.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     lib.rs_model_args.restype = C.c_int
+    lib.rs_model_file.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    lib.rs_model_file.restype = C.c_int
     lib.rs_config_defaults.argtypes = [C.POINTER(Config)]
     lib.rs_config_defaults.restype = None
     lib.rs_host_lp_seeds.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
@@ -180,6 +182,13 @@ class Engine:
         rc = self.lib.rs_model_args(len(argv), arr)
         if rc != 0:
             raise RsError(2, "model rejected its options %r" % (args,))
+
+    def model_file(self, name, data):
+        """Hand the bytes of an input file the model opens inside INIT to the library (before init();
+        data=None forgets the name).  Without it the engine looks for the file in the working directory."""
+        rc = self.lib.rs_model_file(name.encode(), data, len(data) if data is not None else 0)
+        if rc != 0:
+            raise RsError(rc, "rs_model_file(%s)" % name)
 
     def init(self, host_seeds=None, **kw):
         for k, v in kw.items():

@@ -9,6 +9,7 @@ the device engine's digests in its end-to-end steps, at every GPU count, and fai
   python tests/golden/make_checksums.py                 # 1,048,576 LPs, T=100  (~8 min, 5 GB)
   python tests/golden/make_checksums.py 16777216 60     # 16,777,216 LPs, T=60  (~25 min, 30 GB)
   python tests/golden/make_checksums.py 65536 400 - pcs # models/pcs, 65,536 cells, T=400 (BASELINE configs[2], ~7 min)
+  python tests/golden/make_checksums.py 4096 3600 - traffic  # models/traffic on the 4096-LP road grid, one simulated hour
 """
 import json
 import os
@@ -40,7 +41,13 @@ def main():
             env = dict(os.environ, RS_TRACE_OUT=digest, RS_TRACE_HORIZON=repr(T))
             if model == "phold":
                 env["RS_ORACLE_MAX_PAYLOAD"] = "0"
-            subprocess.run([exe, "--lp", str(n), "--seed", str(rs_trace.MASTER_SEED), "--simulation-time", repr(T)], env=env, check=True)
+            if model == "traffic":      # the road grid with this many LPs (make_traffic_topology.py); INIT reads ./topology.txt
+                import make_traffic_topology as mt
+                name = [k for k in mt.GRIDS if mt.n_lps(*mt.GRIDS[k]) == n][0]
+                with open(os.path.join(td, "topology.txt"), "w") as f:
+                    f.write(mt.topology(name)[0])
+            subprocess.run([exe, "--lp", str(n), "--seed", str(rs_trace.MASTER_SEED), "--simulation-time", repr(T)], env=env, check=True,
+                           cwd=td, stdout=subprocess.DEVNULL if model == "traffic" else None)
         cs, total = rs_trace.checksum_digest_file(digest)
     db = json.load(open(OUT)) if os.path.exists(OUT) else {}
     db[key(n, T, model)] = {"model": model, "n_lps": n, "simulation_time": T, "master_seed": rs_trace.MASTER_SEED,

@@ -21,18 +21,30 @@ CASES = [
     ("phold_lp100_T120", "phold", 100, 120, 120, 8),
     ("pcs_lp16_full", "pcs", 16, 0, None, 56),
     ("pcs_lp64_T3000", "pcs", 64, 3000, 3000, 56),
+    # models/traffic on the generated road grids (make_traffic_topology.py; the model reads ./topology.txt in INIT)
+    ("traffic_grid_lp16_T20000", "traffic", 16, 20000, 20000, 8),
+    ("traffic_grid_lp960_T3000", "traffic", 960, 3000, 3000, 8),
 ]
 
 
 def main():
+    only = sys.argv[1:]         # optional: regenerate these models only
     for name, model, lps, simt, hor, sb in CASES:
         import subprocess, tempfile
         exe = os.path.join(rs_trace.ORACLE_REF, model + "_trace")
+        if only and model not in only:
+            continue
         with tempfile.TemporaryDirectory() as td:
             os.makedirs(os.path.join(td, ".rootsim"))
             with open(os.path.join(td, ".rootsim", "numerical.conf"), "w") as f:
                 f.write("%d\n" % rs_trace.MASTER_SEED)
             out = os.path.join(td, "trace.txt")
+            if model == "traffic":
+                import make_traffic_topology
+                text, n = make_traffic_topology.topology(name[:name.rindex("_T")])
+                assert n == lps
+                with open(os.path.join(td, "topology.txt"), "w") as f:
+                    f.write(text)
             env = dict(os.environ, HOME=td, RS_TRACE_OUT=out, RS_TRACE_STATE_BYTES=str(sb))
             if hor is not None:
                 env["RS_TRACE_HORIZON"] = repr(float(hor))

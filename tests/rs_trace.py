@@ -30,8 +30,9 @@ def parse_digest(path):
     return hdr, rows
 
 
-def run_oracle(model, n_lps, sim_time=0.0, horizon=None, portable=True, state_bytes=8, seed=MASTER_SEED, extra=()):
-    """Run oracle/_build/seq[p]_<model>; returns (header, rows, stdout)."""
+def run_oracle(model, n_lps, sim_time=0.0, horizon=None, portable=True, state_bytes=8, seed=MASTER_SEED, extra=(), files=None):
+    """Run oracle/_build/seq[p]_<model>; returns (header, rows, stdout).  files: {name: text} of the input files a
+    model reads inside INIT (written to the working directory of the run)."""
     exe = os.path.join(ORACLE_BUILD, ("seqp_" if portable else "seq_") + model)
     if not os.path.exists(exe):
         raise FileNotFoundError(exe)
@@ -43,12 +44,15 @@ def run_oracle(model, n_lps, sim_time=0.0, horizon=None, portable=True, state_by
         cmd = [exe, "--lp", str(n_lps), "--seed", str(seed)] + list(extra)
         if sim_time:
             cmd += ["--simulation-time", repr(float(sim_time))]
-        r = subprocess.run(cmd, env=env, capture_output=True, text=True, check=True)
+        for fn, text in (files or {}).items():
+            with open(os.path.join(td, fn), "w") as f:
+                f.write(text)
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, check=True, cwd=td)
         hdr, rows = parse_digest(out)
     return hdr, rows, r.stdout
 
 
-def run_reference(model, n_lps, sim_time=0.0, horizon=None, state_bytes=8, seed=MASTER_SEED, extra=(), mode=("--sequential",)):
+def run_reference(model, n_lps, sim_time=0.0, horizon=None, state_bytes=8, seed=MASTER_SEED, extra=(), mode=("--sequential",), files=None):
     """Run the REAL reference built by oracle/build_ref.sh with the tracing shim."""
     exe = os.path.join(ORACLE_REF, model + "_trace")
     if not os.path.exists(exe):
@@ -64,6 +68,9 @@ def run_reference(model, n_lps, sim_time=0.0, horizon=None, state_bytes=8, seed=
         cmd = [exe] + list(mode) + ["--lp", str(n_lps), "--deterministic-seed", "--output-dir", os.path.join(td, "out")] + list(extra)
         if sim_time:
             cmd += ["--simulation-time", str(int(sim_time))]
+        for fn, text in (files or {}).items():
+            with open(os.path.join(td, fn), "w") as f:
+                f.write(text)
         r = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=td)
         if r.returncode != 0:
             raise RuntimeError(r.stdout + r.stderr)

@@ -357,3 +357,105 @@ def test_far_future_events_wait_on_the_far_list(oracle_built, model, n, T, nb, b
         assert rs_trace.compare(rows, orows) == []
     assert st.status & ~0x1 == 0
     assert st.committed_events == sum(r[0] for r in orows)
+
+
+# ---------------------------------------------------------------------------------------------------
+# models/traffic: INIT reads ./topology.txt (models/traffic/init.c:280-313)
+def traffic_topology(name):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_traffic_topology
+    return make_traffic_topology.topology(name)
+
+
+def run_traffic(emu, name, T, wev, **cfg):
+    text, n = traffic_topology(name)
+    lib = rs_host.build_model("traffic", emu=emu)
+    with rs_host.Engine(lib) as eng:
+        eng.model_file("topology.txt", text.encode())
+        eng.init(n_lps=n, master_seed=rs_trace.MASTER_SEED, simulation_time=T, window_events=wev, arena_bytes=1 << 17,
+                 max_payload=16, bucket_width=4.0, n_buckets=4096, **cfg)
+        assert eng.run()
+        st = eng.stats()
+        rows = rs_trace.engine_rows(eng, 8)
+        eng.model_file("topology.txt", None)
+    _, orows, _ = rs_trace.run_oracle("traffic", n, sim_time=T, horizon=T, files={"topology.txt": text})
+    return rows, orows, st
+
+
+@pytest.mark.parametrize("name,T,wev,cfg", [
+    ("traffic_grid_lp16", 20000, 4096, {}),
+    ("traffic_grid_lp960", 3000, 1 << 16, {}),
+    ("traffic_grid_lp960", 1500, 512, dict(ckpt_period=3)),
+    ("traffic_grid_lp4096", 600, 1 << 18, {}),
+])
+def test_traffic_emu_vs_oracle(oracle_built, name, T, wev, cfg):
+    """The reference's models/traffic, sources unchanged: INIT on the engine parses the topology image the host loaded
+    (in-memory fopen/fgets/rewind/strtok_r/strtod), cars are malloc'ed/freed in events, RandomRange, integer abs() of
+    a double, model-local Gaussian through the portable log, exp in the accident probability.  Bit-exact."""
+    if not rs_host.model_sources("traffic") or not os.path.exists(os.path.join(oracle_built, "seqp_traffic")):
+        pytest.skip("traffic sources live in the reference tree")
+    rows, orows, st = run_traffic(True, name, T, wev, **cfg)
+    assert rs_trace.compare(rows, orows) == []
+    assert st.committed_events == sum(r[0] for r in orows)
+    if name != "traffic_grid_lp16":
+        assert st.rollbacks > 0
+
+
+def test_traffic_emu_vs_reference_golden(oracle_built):
+    """Against the UNMODIFIED reference's --sequential digest (libm): integers bit-exact, timestamps within 64 ULP."""
+    if not rs_host.model_sources("traffic"):
+        pytest.skip("traffic sources live in the reference tree")
+    rows, _, _ = run_traffic(True, "traffic_grid_lp960", 3000, 1 << 16)
+    _, grows = rs_trace.parse_digest(os.path.join(os.path.dirname(__file__), "golden", "traffic_grid_lp960_T3000.trace"))
+    assert rs_trace.compare(rows, grows, state_mask=[], ts_ulp=64, check_hash=False) == []
+
+
+def test_missing_input_file_fails_init(oracle_built, tmp_path, monkeypatch):
+    """models/traffic/init.c:289-294: fopen fails -> perror + exit(EXIT_FAILURE).  Here the host notices before INIT."""
+    if not rs_host.model_sources("traffic"):
+        pytest.skip("traffic sources live in the reference tree")
+    monkeypatch.chdir(tmp_path)
+    lib = rs_host.build_model("traffic", emu=True)
+    with rs_host.Engine(lib) as eng:
+        with pytest.raises(rs_host.RsError) as ei:
+            eng.init(n_lps=16, master_seed=1, simulation_time=10.0, arena_bytes=1 << 16, max_payload=16)
+        assert ei.value.code == 5 and "topology.txt" in str(ei.value)
+    # ... and found in the working directory when it is there (what the reference's fopen does)
+    text, n = traffic_topology("traffic_grid_lp16")
+    (tmp_path / "topology.txt").write_text(text)
+    with rs_host.Engine(lib) as eng:
+        eng.init(n_lps=n, master_seed=1, simulation_time=500.0, arena_bytes=1 << 16, max_payload=16, bucket_width=4.0)
+        assert eng.run()
+        assert eng.stats().committed_events > n
+
+
+def test_traffic_makefile_flow_and_cli_emu(oracle_built, tmp_path):
+    """The reference's own build recipe for the model (models/traffic/Makefile: one `rootsim-cc -c` per source, then
+    a link of the objects) and its way of running it: the executable finds ./topology.txt like the reference's."""
+    import subprocess
+    import sys
+    srcs = rs_host.model_sources("traffic")
+    if not srcs:
+        pytest.skip("traffic sources live in the reference tree")
+    cc = [sys.executable, rs_host.ROOTSIM_CC, "--emu"]
+    objs = []
+    for s in srcs:
+        o = str(tmp_path / (os.path.basename(s)[:-2] + ".o"))
+        subprocess.run(cc + ["-Wall", "-Wextra", "-c", s, "-o", o], check=True, capture_output=True, cwd=tmp_path)
+        objs.append(o)
+    subprocess.run(cc + ["-Wall", "-Wextra", "-o", "traffic"] + objs, check=True, capture_output=True, cwd=tmp_path)
+    text, n = traffic_topology("traffic_grid_lp16")
+    (tmp_path / "topology.txt").write_text(text)
+    tr = tmp_path / "trace.txt"
+    r = subprocess.run([str(tmp_path / "traffic"), "--lp", str(n), "--simulation-time", "5000", "--seed", str(rs_trace.MASTER_SEED),
+                        "--wt", "2", "--b200-arena-bytes", "131072", "--b200-max-payload", "16", "--b200-bucket-width", "4",
+                        "--output-dir", str(tmp_path / "out"), "--b200-trace", str(tr)], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0 and "SIMULATION CORRECTLY COMPLETED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "LP 0 (j0.0) is an intersection with 2 neighbours" in r.stdout      # models/traffic/init.c:315
+    _, rows = rs_trace.parse_digest(str(tr))
+    _, orows, _ = rs_trace.run_oracle("traffic", n, sim_time=5000, horizon=5000, files={"topology.txt": text})
+    assert rs_trace.compare(rows, orows) == []
+    os.remove(tmp_path / "topology.txt")
+    r = subprocess.run([str(tmp_path / "traffic"), "--lp", str(n), "--simulation-time", "50"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode != 0 and "topology.txt" in r.stdout + r.stderr

@@ -259,3 +259,52 @@ def test_execution_modes_commit_the_same_trace(oracle_built, cfg):
     _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
     assert rs_trace.compare(rows, orows, state_mask=PHOLD_MASK) == []
     assert st.status & ~0x1 == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# models/traffic (BASELINE config 5): INIT reads ./topology.txt
+def run_traffic_gpu(name, T, wev, **cfg):
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_traffic_topology
+    text, n = make_traffic_topology.topology(name)
+    lib = rs_host.build_model("traffic")
+    with rs_host.Engine(lib) as eng:
+        assert eng.info().engine == b"cuda-sm100a"
+        eng.model_file("topology.txt", text.encode())
+        eng.init(n_lps=n, master_seed=rs_trace.MASTER_SEED, simulation_time=T, window_events=wev, arena_bytes=1 << 17,
+                 max_payload=16, bucket_width=4.0, n_buckets=4096, **cfg)
+        assert eng.run()
+        st = eng.stats()
+        rows = rs_trace.engine_rows(eng, 8)
+        eng.model_file("topology.txt", None)
+    return rows, st, text, n
+
+
+@pytest.mark.parametrize("name,T,wev,cfg", [
+    ("traffic_grid_lp16", 20000, 4096, {}),
+    ("traffic_grid_lp960", 3000, 1 << 16, {}),
+    ("traffic_grid_lp960", 1500, 512, dict(ckpt_period=3)),
+    ("traffic_grid_lp4096", 2000, 1 << 18, {}),
+])
+def test_traffic_vs_oracle(oracle_built, name, T, wev, cfg):
+    """The reference's models/traffic, sources unchanged.  INIT runs on the device and parses the topology image the
+    host loaded (in-memory fopen/fgets/rewind/strtok_r/strtod of csrc/rs_prelude.cuh); cars are malloc'ed and freed
+    inside events, the queue is a linked list in the LP's heap (up to 1000 cars of 64 bytes at a junction).
+    Compared bit-exactly: counts, event hash, timestamps, RNG seeds, lvt in the state."""
+    need("traffic", oracle_built)
+    rows, st, text, n = run_traffic_gpu(name, T, wev, **cfg)
+    _, orows, _ = rs_trace.run_oracle("traffic", n, sim_time=T, horizon=T, files={"topology.txt": text})
+    assert rs_trace.compare(rows, orows) == []
+    assert st.committed_events == sum(r[0] for r in orows)
+    assert st.kernel_launches > 0
+
+
+def test_traffic_vs_reference_golden(oracle_built):
+    """Against the UNMODIFIED reference's --sequential digest (tests/golden, libm log/exp): integers bit-exact,
+    timestamps within 64 ULP."""
+    need("traffic", oracle_built)
+    for name, gold, T in (("traffic_grid_lp16", "traffic_grid_lp16_T20000", 20000), ("traffic_grid_lp960", "traffic_grid_lp960_T3000", 3000)):
+        rows, _, _, _ = run_traffic_gpu(name, T, 1 << 16)
+        _, grows = rs_trace.parse_digest(os.path.join(GOLD, gold + ".trace"))
+        assert rs_trace.compare(rows, grows, state_mask=[], ts_ulp=64, check_hash=False) == []

@@ -18,7 +18,20 @@ CASES = [
     ("phold_lp100_T120", "phold", 100, 120, 120, 8, PHOLD_MASK),
     ("pcs_lp16_full", "pcs", 16, 0, None, 56, PCS_MASK),
     ("pcs_lp64_T3000", "pcs", 64, 3000, 3000, 56, PCS_MASK),
+    # models/traffic on generated road grids (state: the first 8 bytes are lp_state_type.lvt)
+    ("traffic_grid_lp16_T20000", "traffic", 16, 20000, 20000, 8, None),
+    ("traffic_grid_lp960_T3000", "traffic", 960, 3000, 3000, 8, None),
 ]
+
+
+def model_files(name, model):
+    """Input files a model reads inside INIT (models/traffic/init.c:289 opens ./topology.txt)."""
+    if model != "traffic":
+        return None
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_traffic_topology
+    return {"topology.txt": make_traffic_topology.topology(name[:name.rindex("_T")])[0]}
 
 
 @pytest.mark.parametrize("name,model,lps,simt,hor,sb,mask", CASES, ids=[c[0] for c in CASES])
@@ -26,7 +39,8 @@ def test_oracle_matches_golden(oracle_built, name, model, lps, simt, hor, sb, ma
     if not os.path.exists(os.path.join(oracle_built, "seq_" + model)):
         pytest.skip("oracle for %s not built (model sources live in the reference tree)" % model)
     ghdr, grows = rs_trace.parse_digest(os.path.join(GOLD, name + ".trace"))
-    hdr, rows, _ = rs_trace.run_oracle(model, lps, sim_time=simt, horizon=hor, portable=False, state_bytes=sb)
+    hdr, rows, _ = rs_trace.run_oracle(model, lps, sim_time=simt, horizon=hor, portable=False, state_bytes=sb,
+                                       files=model_files(name, model))
     assert hdr["total"] == ghdr["total"]
     assert rs_trace.compare(rows, grows, state_mask=mask) == []
 
@@ -38,6 +52,29 @@ def test_oracle_matches_live_reference_phold(oracle_built, lps, simt):
     _, ref_rows, _ = rs_trace.run_reference("phold", lps, sim_time=simt, horizon=simt)
     _, rows, _ = rs_trace.run_oracle("phold", lps, sim_time=simt, horizon=simt, portable=False)
     assert rs_trace.compare(rows, ref_rows, state_mask=PHOLD_MASK) == []
+
+
+def test_oracle_matches_live_reference_traffic(oracle_built):
+    """models/traffic: INIT parses a file, cars are malloc'ed and freed inside events, RandomRange, a model-local
+    Gaussian (log, sqrt), C's integer abs() on a double, exp() in the accident probability."""
+    if not have_reference_binary("traffic"):
+        pytest.skip("oracle/_ref not built")
+    files = model_files("traffic_grid_lp960_T1500", "traffic")
+    _, ref_rows, _ = rs_trace.run_reference("traffic", 960, sim_time=1500, horizon=1500, files=files)
+    _, rows, _ = rs_trace.run_oracle("traffic", 960, sim_time=1500, horizon=1500, portable=False, files=files)
+    assert rs_trace.compare(rows, ref_rows) == []
+    assert sum(r[0] for r in rows) > 100000
+
+
+def test_portable_math_changes_only_ulps_traffic(oracle_built):
+    """models/traffic with rs_math.h's log AND exp in the model's own calls (the flavour the device is compared with
+    bit-exactly): every integer of the trace equals the libm flavour's, timestamps stay within 64 ULP."""
+    if not os.path.exists(os.path.join(oracle_built, "seq_traffic")):
+        pytest.skip("traffic oracle not built")
+    files = model_files("traffic_grid_lp960_T3000", "traffic")
+    _, a, _ = rs_trace.run_oracle("traffic", 960, sim_time=3000, horizon=3000, portable=False, files=files)
+    _, b, _ = rs_trace.run_oracle("traffic", 960, sim_time=3000, horizon=3000, portable=True, files=files)
+    assert rs_trace.compare(a, b, state_mask=[], ts_ulp=64, check_hash=False) == []
 
 
 def test_portable_log_changes_only_ulps(oracle_built):

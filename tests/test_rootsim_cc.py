@@ -65,3 +65,37 @@ def test_vla_rewrite():
     out = cc.rewrite_vlas(src, {"num_buffers"})
     assert "rs_vla<buffers *, RS_VLA_CAP> pointers(num_buffers);" in out
     assert "int fixed[8];" in out
+
+
+def test_cxx_keywords_used_as_c_identifiers_are_renamed():
+    """models/traffic/functions.c:393 has a parameter called `new`; the unity source is C++."""
+    cc = load_cc()
+    src = 'void f(int id, double new) { /* new in a comment */ g(id, new); printf("new\\n"); }\nstruct s { int class; int newer; };\n'
+    out = cc.rename_cxx_keywords(src)
+    assert "double new_)" in out and "g(id, new_);" in out and "int class_;" in out
+    assert "/* new in a comment */" in out and '"new\\n"' in out and "int newer;" in out
+
+
+def test_input_files_of_a_model_are_found():
+    """fopen(<literal or macro of one>, "r") names a file the engine loads before INIT (models/traffic/init.h:23,
+    init.c:289); files opened for writing, or under a computed name, are not input images."""
+    cc = load_cc()
+    hdr = '#define FILENAME\t"topology.txt"\n#define OTHER 12\n'
+    src = ('void init(void) { FILE *f = fopen(FILENAME, "r"); FILE *g = fopen("cfg/extra.dat", "rb");\n'
+           ' FILE *w = fopen("out.txt", "w"); FILE *c = fopen(name, "r"); /* fopen("ghost", "r") */ }\n')
+    assert cc.input_files([hdr, src]) == ["topology.txt", "cfg/extra.dat"]
+
+
+def test_compile_only_objects_name_their_source(tmp_path, monkeypatch):
+    """The reference's model Makefiles run `rootsim-cc -c x.c -o x.o` per file and link the objects
+    (models/traffic/Makefile:13-17); here the link step rebuilds the unity source from what the objects name."""
+    cc = load_cc()
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "a.c").write_text("int x;\n")
+    (tmp_path / "b.c").write_text("int y;\n")
+    assert cc.main(["-Wall", "-Wextra", "-c", "a.c", "-o", "a.o"]) == 0
+    assert cc.main(["-c", "b.c"]) == 0
+    assert (tmp_path / "a.o").read_text().split() == [cc.STUB_MAGIC, str(tmp_path / "a.c")]
+    assert (tmp_path / "b.o").read_text().split() == [cc.STUB_MAGIC, str(tmp_path / "b.c")]
+    (tmp_path / "foreign.o").write_bytes(b"\x7fELF....")
+    assert cc.main(["-o", "model", "foreign.o"]) == 1

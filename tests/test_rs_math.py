@@ -36,3 +36,36 @@ def test_rs_log_within_one_ulp_of_libm():
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) <= 1
     assert out[1] == "0x0p+0"
+
+
+SRC_EXP = r"""
+#include <stdio.h>
+#include <math.h>
+#include <rs_math.h>
+int main(void) {
+  unsigned long long s = 88172645463325252ULL, maxulp = 0;
+  for (long i = 0; i < 4000000; i++) {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    double u = ((s >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+    /* the range models/traffic/normal_cdf.c uses (-0.5 x^2, |x| < 37.6), small arguments, and the full range */
+    double x = (i % 3 == 0) ? -704.0 * u : (i % 3 == 1) ? 2.0 * u - 1.0 : 1400.0 * u - 700.0;
+    long long a = (long long)rs_d2u(rs_exp(x)), b = (long long)rs_d2u(exp(x));
+    unsigned long long d = a > b ? a - b : b - a;
+    if (d > maxulp) maxulp = d;
+  }
+  printf("%llu %a %a %a %a\n", maxulp, rs_exp(0.0), rs_exp(-800.0), rs_exp(800.0), rs_exp(-740.0));
+  return 0;
+}
+"""
+
+
+def test_rs_exp_within_one_ulp_of_libm():
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(SRC_EXP)
+        exe = os.path.join(td, "t")
+        subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-I", os.path.join(REPO, "root-sim_b200", "include"), c, "-o", exe, "-lm"], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) <= 1
+    assert out[1] == "0x1p+0" and out[2] == "0x0p+0" and out[3] == "inf"
+    assert float.fromhex(out[4]) > 0.0          # subnormal result, scaled in two steps
