@@ -277,12 +277,12 @@ def run_ours(args):
         pcs = pcs_block(rs_host, rs_trace)
 
     # SURVEY.md section 8(f) rank 3 (BASELINE config 5): models/traffic on a generated road grid
-    traffic = None
+    traffic_row = None
     if world == 1 and not args.no_traffic:
         try:
-            traffic = traffic_block(rs_host, rs_trace)
+            traffic_row = traffic_block(rs_host, rs_trace)
         except Exception as ex:         # a widened row never costs the headline line
-            traffic = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:300]), "parity_checksum_ok": None}
+            traffic_row = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:300]), "parity_checksum_ok": None}
 
     parity_ok, gold = None, None
     for x in e2e_steps:
@@ -359,8 +359,8 @@ def run_ours(args):
         line["supplementary"] = sup
     if pcs:
         line["pcs"] = pcs
-    if traffic:
-        line["traffic"] = traffic
+    if traffic_row:
+        line["traffic_model"] = traffic_row
     if secondary:
         line["secondary"] = secondary
     if rank == 0:
@@ -371,7 +371,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if parity_ok is False or (secondary and secondary["parity_checksum_ok"] is False) or (pcs and pcs["parity_checksum_ok"] is False) \
-            or (traffic and traffic["parity_checksum_ok"] is False):
+            or (traffic_row and traffic_row["parity_checksum_ok"] is False):
         print("bench.py: PARITY CHECKSUM MISMATCH against the oracle", file=sys.stderr)
         sys.exit(3)
 

@@ -77,7 +77,7 @@ build_model() { # model name, extra-cflags, suffix, extra objects
 }
 
 gcc $CF $DEFS -c "$HERE/trace_shim.c" -o "$OUT/obj/trace_shim.o"
-for m in ${RS_REF_MODELS:-phold pcs traffic}; do
+for m in ${RS_REF_MODELS:-phold pcs traffic packet collector}; do
 	build_model "$m" "-DOnGVT=OnGVT_light -DProcessEvent=ProcessEvent_light" ""
 	build_model "$m" "-DOnGVT=OnGVT_model -DProcessEvent=ProcessEvent_model" "_trace" "$OUT/obj/trace_shim.o"
 done

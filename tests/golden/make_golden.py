@@ -21,6 +21,10 @@ CASES = [
     ("phold_lp100_T120", "phold", 100, 120, 120, 8),
     ("pcs_lp16_full", "pcs", 16, 0, None, 56),
     ("pcs_lp64_T3000", "pcs", 64, 3000, 3000, 56),
+    # models/packet (graph topology, 24-byte payload that carries a pointer) and models/collector (star topology: LP 0
+    # receives everything); horizons below the models' own termination (OnGVT)
+    ("packet_lp256_T20000", "packet", 256, 20000, 20000, 4),
+    ("collector_lp256_T400", "collector", 256, 400, 400, 4),
     # models/traffic on the generated road grids (make_traffic_topology.py; the model reads ./topology.txt in INIT)
     ("traffic_grid_lp16_T20000", "traffic", 16, 20000, 20000, 8),
     ("traffic_grid_lp960_T3000", "traffic", 960, 3000, 3000, 8),

@@ -459,3 +459,17 @@ def test_traffic_makefile_flow_and_cli_emu(oracle_built, tmp_path):
     os.remove(tmp_path / "topology.txt")
     r = subprocess.run([str(tmp_path / "traffic"), "--lp", str(n), "--simulation-time", "50"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode != 0 and "topology.txt" in r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("model,n,T,wev", [("packet", 256, 20000, 4096), ("packet", 5000, 2000, 1 << 16), ("collector", 256, 400, 4096),
+                                           ("collector", 4000, 25, 1 << 16)])
+def test_small_reference_models_emu_vs_oracle(oracle_built, model, n, T, wev):
+    """models/packet (TOPOLOGY_GRAPH, 24-byte payload with a pointer in it, two mallocs in INIT) and models/collector
+    (TOPOLOGY_STAR: every LP sends to LP 0, which becomes one long event chain) -- reference sources unchanged,
+    horizons below the models' own OnGVT termination."""
+    if not rs_host.model_sources(model) or not os.path.exists(os.path.join(oracle_built, "seqp_" + model)):
+        pytest.skip("%s sources live in the reference tree" % model)
+    rows, st = run_emu(model, n, T, wev, state_bytes=4, arena_bytes=256, max_payload=32, bucket_width=8.0, n_buckets=4096)
+    _, orows, _ = rs_trace.run_oracle(model, n, sim_time=T, horizon=T, state_bytes=4)
+    assert rs_trace.compare(rows, orows) == []
+    assert st.committed_events == sum(r[0] for r in orows)

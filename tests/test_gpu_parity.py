@@ -308,3 +308,15 @@ def test_traffic_vs_reference_golden(oracle_built):
         rows, _, _, _ = run_traffic_gpu(name, T, 1 << 16)
         _, grows = rs_trace.parse_digest(os.path.join(GOLD, gold + ".trace"))
         assert rs_trace.compare(rows, grows, state_mask=[], ts_ulp=64, check_hash=False) == []
+
+
+@pytest.mark.parametrize("model,n,T,wev", [("packet", 256, 20000, 4096), ("packet", 65536, 1500, 1 << 18), ("collector", 256, 400, 4096),
+                                           ("collector", 4000, 25, 1 << 16)])
+def test_small_reference_models_vs_oracle(oracle_built, model, n, T, wev):
+    """models/packet (TOPOLOGY_GRAPH, 24-byte payloads) and models/collector (TOPOLOGY_STAR: LP 0 receives everything),
+    reference sources unchanged, horizons below the models' own OnGVT termination.  Bit-exact."""
+    need(model, oracle_built)
+    rows, st = run_gpu(model, n, T, state_bytes=4, window_events=wev, arena_bytes=256, max_payload=32, bucket_width=8.0, n_buckets=4096)
+    _, orows, _ = rs_trace.run_oracle(model, n, sim_time=T, horizon=T, state_bytes=4)
+    assert rs_trace.compare(rows, orows) == []
+    assert st.committed_events == sum(r[0] for r in orows)

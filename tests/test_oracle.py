@@ -18,6 +18,8 @@ CASES = [
     ("phold_lp100_T120", "phold", 100, 120, 120, 8, PHOLD_MASK),
     ("pcs_lp16_full", "pcs", 16, 0, None, 56, PCS_MASK),
     ("pcs_lp64_T3000", "pcs", 64, 3000, 3000, 56, PCS_MASK),
+    ("packet_lp256_T20000", "packet", 256, 20000, 20000, 4, None),           # state: packet_count
+    ("collector_lp256_T400", "collector", 256, 400, 400, 4, None),
     # models/traffic on generated road grids (state: the first 8 bytes are lp_state_type.lvt)
     ("traffic_grid_lp16_T20000", "traffic", 16, 20000, 20000, 8, None),
     ("traffic_grid_lp960_T3000", "traffic", 960, 3000, 3000, 8, None),
