@@ -39,6 +39,8 @@ def main():
     lib = rs_host.lib_path(spec["model"], emu=True)
     eng = rs_host.Engine(lib, private=True)
     eng.model_args(spec.get("margs", []))
+    for fn, text in spec.get("files", {}).items():      # input files the model reads inside INIT: every rank loads them
+        eng.model_file(fn, text.encode())
     first, count = rs_host.lp_block(eng.lib, spec["n"], world, rank)
     cfg = dict(spec["cfg"], n_lps=spec["n"], rank=rank, nranks=world, lp_first=first, lp_count=count)
     eng.init(**cfg)

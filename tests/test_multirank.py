@@ -96,3 +96,22 @@ def test_fatal_status_on_one_rank_stops_all_ranks(oracle_built, tmp_path):
     names = [set(g["status_names"]) for g in got]
     assert any("XCHG_FULL" in s for s in names)
     assert all(("XCHG_FULL" in s) or ("PEER_FATAL" in s) for s in names)
+
+
+@pytest.mark.parametrize("world,name,T", [(2, "traffic_grid_lp960", 2000), (3, "traffic_grid_lp16", 20000)])
+def test_traffic_multirank_vs_oracle(oracle_built, tmp_path, world, name, T):
+    """models/traffic over several ranks: every rank loads the topology image and runs INIT for its own block of LPs
+    (neighbour ids are global), cars cross ranks inside 16-byte payloads, antimessages travel between ranks."""
+    if not rs_host.model_sources("traffic") or not os.path.exists(os.path.join(oracle_built, "seqp_traffic")):
+        pytest.skip("traffic sources live in the reference tree")
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_traffic_topology
+    text, n = make_traffic_topology.topology(name)
+    rs_host.build_model("traffic", emu=True)
+    spec = {"model": "traffic", "n": n, "state_bytes": 8, "files": {"topology.txt": text},
+            "cfg": dict(master_seed=rs_trace.MASTER_SEED, simulation_time=float(T), window_events=1 << 14, arena_bytes=1 << 17,
+                        max_payload=16, bucket_width=4.0, n_buckets=4096)}
+    rows, got = run_ranks(world, spec, tmp_path)
+    _, orows, _ = rs_trace.run_oracle("traffic", n, sim_time=T, horizon=T, files={"topology.txt": text})
+    assert rs_trace.compare(rows, orows) == []
+    assert sum(g["stats"]["committed_events"] for g in got) == sum(r[0] for r in orows)

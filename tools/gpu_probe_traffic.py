@@ -47,6 +47,9 @@ def run(flags=0, **cfg):
     return kt
 
 
+if os.environ.get("RS_PROBE_ONE") == "1":     # one run of the bench configuration (for a profiler)
+    run()
+    sys.exit(0)
 run()
 run(window_events=1 << 14)
 run(window_events=1 << 16, bucket_width=1.0)
