@@ -521,9 +521,26 @@ def cpu_baseline(runs):
                 secs = float([l for l in txt.split("\n") if l.startswith("TOTAL SIMULATION TIME")][0].split(":")[1].split()[0])
                 v = committed / secs
                 best = v if best is None else max(best, v)
-        return {"value": best, "unit": "events/s", "cores": wt, "kind": "reference",
-                "sample": "unmodified ROOT-Sim 2.0.0 (oracle/_ref/phold) --wt %d --lp 1024 --simulation-time 150; the reference "
-                          "cannot run 1M LPs (MAX_LPs 250000, 4 MiB stack per LP)" % wt}
+        out = {"value": best, "unit": "events/s", "cores": wt, "kind": "reference",
+               "sample": "unmodified ROOT-Sim 2.0.0 (oracle/_ref/phold) --wt %d --lp 1024 --simulation-time 150; the reference "
+                         "cannot run 1M LPs (MAX_LPs 250000, 4 MiB stack per LP)" % wt}
+        # the reference's own sequential engine on the same sample (one core).  Larger LP counts are
+        # left out: `--wt 8 --lp 4096 --simulation-time 100` does not finish in two minutes (O(#LP) LP lookup per event,
+        # src/scheduler/process.c:157-164; 16 GB of stacks)
+        try:
+            with tempfile.TemporaryDirectory() as td:
+                os.makedirs(os.path.join(td, ".rootsim"))
+                open(os.path.join(td, ".rootsim", "numerical.conf"), "w").write("%d\n" % MASTER_SEED)
+                subprocess.run([exe, "--sequential", "--lp", "1024", "--simulation-time", "150", "--deterministic-seed",
+                                "--output-dir", os.path.join(td, "o")], env=dict(os.environ, HOME=td), cwd=td, capture_output=True, text=True, timeout=120)
+                txt = open(os.path.join(td, "o", "sequential_stats")).read()
+                events = float([l for l in txt.split("\n") if l.startswith("TOTAL EXECUTED EVENTS")][0].split(":")[1])
+                secs = float([l for l in txt.split("\n") if l.startswith("TOTAL SIMULATION TIME")][0].split(":")[1].split()[0])
+                out["sequential"] = {"value": events / secs, "unit": "events/s", "cores": 1,
+                                     "sample": "unmodified ROOT-Sim 2.0.0 --sequential --lp 1024 --simulation-time 150"}
+        except Exception as ex:
+            out["sequential"] = {"unavailable": str(ex)[:200]}
+        return out
     import rs_trace
     _, _, out = rs_trace.run_oracle("phold", 65536, sim_time=60, horizon=60)
     v = float(out.strip().split("events_per_s=")[1].split()[0])
