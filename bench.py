@@ -284,6 +284,17 @@ def run_ours(args):
         except Exception as ex:         # a widened row never costs the headline line
             traffic_row = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:300]), "parity_checksum_ok": None}
 
+    # BASELINE.json configs[4] (C5): the same model on several GPUs, 68,608-LP road grid, one checked run (the flow of
+    # tools/multigpu_check_traffic.py: every rank loads the topology image and runs INIT for its own LPs)
+    if world > 1 and not args.no_traffic:
+        try:
+            sys.path.insert(0, os.path.join(REPO, "tools"))
+            import multigpu_check_traffic
+            traffic_row = multigpu_check_traffic.run(os.environ.get("RS_BENCH_TRAFFIC_GRID", "traffic_grid_lp68608"), 3600.0,
+                                                     rank, world, local, dist, torch)
+        except Exception as ex:         # a widened row never costs the headline line
+            traffic_row = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:300]), "parity_checksum_ok": None}
+
     parity_ok, gold = None, None
     for x in e2e_steps:
         ok, gold = check_parity(x, n_lps, T)
