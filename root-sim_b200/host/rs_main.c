@@ -77,6 +77,29 @@ static const char *trace_file;
 static bool deterministic_seed, seed_given, verbose;
 static bool stats_lp = true;	/* --stats all (the reference's default) or lp: per-LP rows in thread_0_0/lps */
 
+static int arena_given, payload_given;
+
+/* The reference gives a model whatever it mallocs and sends (DyMeLoR grows, src/mm/dymelor.c:172-350; message
+ * slabs of 512 bytes, src/communication/communication.c:431-449).  Here the per-LP heap and the payload slot are
+ * fixed at engine creation.  When a run stops because one of them was too small and the user did not size it, the run is
+ * started again from the beginning with twice the size (a simulation is a function of its seed: nothing is lost but
+ * the time of the short run).  Returns 1 when a restart makes sense. */
+static int grow_model_memory(unsigned status_bits)
+{
+	int again = 0;
+	if ((status_bits & RS_ST_ARENA_FULL) && !arena_given && cfg.arena_bytes < (1u << 22)) {
+		cfg.arena_bytes *= 2;
+		fprintf(stderr, "[b200] the model's per-LP heap did not fit: restarting with --b200-arena-bytes %u\n", cfg.arena_bytes);
+		again = 1;
+	}
+	if ((status_bits & RS_ST_PAYLOAD) && !payload_given && cfg.max_payload < 512u) {
+		cfg.max_payload = cfg.max_payload ? 2 * cfg.max_payload : 16;
+		fprintf(stderr, "[b200] an event payload did not fit: restarting with --b200-max-payload %u\n", cfg.max_payload);
+		again = 1;
+	}
+	return again;
+}
+
 static error_t parse_opt(int key, char *arg, struct argp_state *state)
 {
 	switch (key) {
@@ -111,8 +134,8 @@ static error_t parse_opt(int key, char *arg, struct argp_state *state)
 	case OPT_B_NBUCKETS: cfg.n_buckets = (uint32_t)strtoul(arg, NULL, 10); break;
 	case OPT_B_WINDOW: cfg.window_events = (uint32_t)strtoul(arg, NULL, 10); break;
 	case OPT_B_PENDING: cfg.max_pending = strtoull(arg, NULL, 10); break;
-	case OPT_B_ARENA: cfg.arena_bytes = (uint32_t)strtoul(arg, NULL, 10); break;
-	case OPT_B_PAYLOAD: cfg.max_payload = (uint32_t)strtoul(arg, NULL, 10); break;
+	case OPT_B_ARENA: cfg.arena_bytes = (uint32_t)strtoul(arg, NULL, 10); arena_given = 1; break;
+	case OPT_B_PAYLOAD: cfg.max_payload = (uint32_t)strtoul(arg, NULL, 10); payload_given = 1; break;
 	case OPT_B_DEVICE: cfg.device = atoi(arg); break;
 	case OPT_B_TRACE: trace_file = arg; break;
 	case OPT_B_SPAN: cfg.window_span = atof(arg); break;
@@ -188,12 +211,31 @@ int main(int argc, char **argv)
 
 	if (!seed_given)
 		cfg.master_seed = load_master_seed();
+	if (!arena_given && cfg.n_lps) {
+		/* default per-LP heap: 8 GiB of HBM shared by the LPs, between 256 bytes and 128 KiB each (a power of two);
+		 * a checkpoint copies the used prefix only, so room that a model does not use costs memory, not bandwidth */
+		unsigned long long a = (8ull << 30) / cfg.n_lps;
+		uint32_t p = 256;
+		while (p < (128u << 10) && 2ull * p <= a)
+			p *= 2;
+		cfg.arena_bytes = p;
+	}
 
 	char t_start[64], t_end[64];
+	int attempts = 0;
+restart:
 	stamp(t_start, sizeof t_start);
 	rs_engine_t *eng = NULL;
 	int rc = rs_dev_init(&cfg, NULL, &eng);
 	if (rc != RS_OK) {
+		unsigned bits = 0;
+		const char *msg = rs_dev_error(eng), *hex = msg ? strstr(msg, "status 0x") : NULL;
+		if (hex)
+			sscanf(hex + 7, "%x", &bits);
+		if (attempts++ < 16 && grow_model_memory(bits)) {
+			rs_dev_fini(eng);
+			goto restart;
+		}
 		fprintf(stderr, "rs_dev_init failed (%d): %s\n", rc, rs_dev_error(eng));
 		printf("\n--------- SIMULATION ABNORMALLY TERMINATED ----------\n");
 		return EXIT_FAILURE;
@@ -233,6 +275,11 @@ int main(int argc, char **argv)
 		}
 	}
 	rs_dev_stats(eng, &st);
+	if (rc != RS_OK && attempts++ < 16 && grow_model_memory(st.status)) {
+		free(gvt_rows);
+		rs_dev_fini(eng);
+		goto restart;
+	}
 	stamp(t_end, sizeof t_end);
 	if (rc != RS_OK)
 		fprintf(stderr, "simulation error (%d): %s\n", rc, rs_dev_error(eng));

@@ -22,7 +22,8 @@ static void check_strtod(const char *s)
 int main(void)
 {
 	const char *fixed[] = { "60", "0.5", "-1", "1", "1.5", "0.05", "3.25e2", "  12.75xyz", "abc", "", ".", "-", "+.5", "5.", "1e", "1e+", "1e5",
-				"0.000123", "123456789012345", "9007199254740991", "-0", "1E-5", "007", "1.0e22", "4.2.1", "1e-22" };
+				"0.000123", "123456789012345", "9007199254740991", "-0", "1E-5", "007", "1.0e22", "4.2.1", "1e-22", "1e999", "-1e999",
+				"1e-999", "0e999" };
 	for (unsigned i = 0; i < sizeof(fixed) / sizeof(fixed[0]); i++)
 		check_strtod(fixed[i]);
 	/* decimals with at most 15 significant digits and a small exponent: correctly rounded, i.e. glibc's bits */

@@ -449,9 +449,11 @@ def test_traffic_makefile_flow_and_cli_emu(oracle_built, tmp_path):
     (tmp_path / "topology.txt").write_text(text)
     tr = tmp_path / "trace.txt"
     r = subprocess.run([str(tmp_path / "traffic"), "--lp", str(n), "--simulation-time", "5000", "--seed", str(rs_trace.MASTER_SEED),
-                        "--wt", "2", "--b200-arena-bytes", "131072", "--b200-max-payload", "16", "--b200-bucket-width", "4",
-                        "--output-dir", str(tmp_path / "out"), "--b200-trace", str(tr)], capture_output=True, text=True, cwd=tmp_path)
+                        "--wt", "2", "--output-dir", str(tmp_path / "out"), "--b200-trace", str(tr)], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 0 and "SIMULATION CORRECTLY COMPLETED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    # no device sizing on the command line, as with the reference: the per-LP heap defaults to a share of 8 GiB, and the
+    # run that found its 0-byte payload slots too small was started again with room for the model's 16-byte payloads
+    assert "restarting with --b200-max-payload 16" in r.stderr
     assert "LP 0 (j0.0) is an intersection with 2 neighbours" in r.stdout      # models/traffic/init.c:315
     _, rows = rs_trace.parse_digest(str(tr))
     _, orows, _ = rs_trace.run_oracle("traffic", n, sim_time=5000, horizon=5000, files={"topology.txt": text})
