@@ -475,3 +475,31 @@ def test_small_reference_models_emu_vs_oracle(oracle_built, model, n, T, wev):
     _, orows, _ = rs_trace.run_oracle(model, n, sim_time=T, horizon=T, state_bytes=4)
     assert rs_trace.compare(rows, orows) == []
     assert st.committed_events == sum(r[0] for r in orows)
+
+
+def test_traffic_shipped_topology_emu_vs_oracle_and_reference(oracle_built):
+    """The topology the reference ships (models/traffic/topology.txt: the Italian motorway graph, 62 junctions + 962
+    one-km segments = 1024 LPs), where the reference tree is present: engine = oracle bit for bit, oracle (libm) = the
+    unmodified reference's --sequential run bit for bit."""
+    from conftest import have_reference_binary
+    path = os.path.join(os.environ.get("RS_REFERENCE", "/root/reference"), "models", "traffic", "topology.txt")
+    if not os.path.exists(path) or not rs_host.model_sources("traffic"):
+        pytest.skip("the reference tree is not here")
+    text = open(path).read()
+    n, T = 1024, 3600
+    lib = rs_host.build_model("traffic", emu=True)
+    with rs_host.Engine(lib) as eng:
+        eng.model_file("topology.txt", text.encode())
+        eng.init(n_lps=n, master_seed=rs_trace.MASTER_SEED, simulation_time=float(T), window_events=1 << 16, arena_bytes=1 << 17,
+                 max_payload=16, bucket_width=4.0, n_buckets=4096)
+        assert eng.run()
+        rows = rs_trace.engine_rows(eng, 8)
+        eng.model_file("topology.txt", None)
+    _, orows, _ = rs_trace.run_oracle("traffic", n, sim_time=T, horizon=T, files={"topology.txt": text})
+    assert rs_trace.compare(rows, orows) == []
+    assert sum(r[0] for r in orows) > 300000
+    if have_reference_binary("traffic"):
+        _, lrows, _ = rs_trace.run_oracle("traffic", n, sim_time=T, horizon=T, files={"topology.txt": text}, portable=False)
+        _, rrows, _ = rs_trace.run_reference("traffic", n, sim_time=T, horizon=T, files={"topology.txt": text})
+        assert rs_trace.compare(lrows, rrows) == []
+        assert rs_trace.compare(rows, rrows, state_mask=[], ts_ulp=64, check_hash=False) == []

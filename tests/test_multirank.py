@@ -98,7 +98,7 @@ def test_fatal_status_on_one_rank_stops_all_ranks(oracle_built, tmp_path):
     assert all(("XCHG_FULL" in s) or ("PEER_FATAL" in s) for s in names)
 
 
-@pytest.mark.parametrize("world,name,T", [(2, "traffic_grid_lp960", 2000), (3, "traffic_grid_lp16", 20000)])
+@pytest.mark.parametrize("world,name,T", [(2, "traffic_grid_lp960", 2000), (3, "traffic_grid_lp16", 20000), (4, "traffic_grid_lp960", 1000)])
 def test_traffic_multirank_vs_oracle(oracle_built, tmp_path, world, name, T):
     """models/traffic over several ranks: every rank loads the topology image and runs INIT for its own block of LPs
     (neighbour ids are global), cars cross ranks inside 16-byte payloads, antimessages travel between ranks."""
