@@ -55,7 +55,7 @@ static const struct argp_option options[] = {
 	{"serial", OPT_SERIAL, 0, 0, "Not available: this runtime is the optimistic device engine", 0},
 	{"sequential", OPT_SEQUENTIAL, 0, 0, "Alias for --serial", 0},
 	{"no-core-binding", OPT_NO_CORE_BINDING, 0, 0, "Accepted, ignored", 0},
-	{"verbose", OPT_VERBOSE, "TYPE", OPTION_ARG_OPTIONAL, "Verbose execution", 0},
+	{"verbose", OPT_VERBOSE, "TYPE", 0, "Verbose execution (info, debug: a TIME BARRIER line per batch of windows; no: quiet), src/core/init.c:170", 0},
 	{"stats", OPT_STATS, "TYPE", 0, "Level of detail in the output statistics", 0},
 	{"b200-bucket-width", OPT_B_BUCKET, "T", 0, "Calendar bucket width in simulated time (power of two)", 1},
 	{"b200-buckets", OPT_B_NBUCKETS, "N", 0, "Calendar ring size", 1},
@@ -123,7 +123,7 @@ static error_t parse_opt(int key, char *arg, struct argp_state *state)
 	case OPT_SERIAL: case OPT_SEQUENTIAL:
 		argp_error(state, "--sequential is not available: this runtime is the optimistic B200 engine");
 		break;
-	case OPT_VERBOSE: verbose = true; break;
+	case OPT_VERBOSE: verbose = strcmp(arg, "no") != 0; break;
 	case OPT_STATS:		/* src/core/init.c:213-215: all | performance | lp | global */
 		stats_lp = (!strcmp(arg, "all") || !strcmp(arg, "lp"));
 		break;
