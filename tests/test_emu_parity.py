@@ -503,3 +503,17 @@ def test_traffic_shipped_topology_emu_vs_oracle_and_reference(oracle_built):
         _, rrows, _ = rs_trace.run_reference("traffic", n, sim_time=T, horizon=T, files={"topology.txt": text})
         assert rs_trace.compare(lrows, rrows) == []
         assert rs_trace.compare(rows, rrows, state_mask=[], ts_ulp=64, check_hash=False) == []
+
+
+@pytest.mark.parametrize("n,T,wev,cfg", [(200, 300, 4096, {}), (1000, 100, 100000, {}), (50, 3000, 512, dict(ckpt_period=1)), (64, 400, 64, dict(ckpt_period=1000))])
+def test_heap_stress_emu_vs_oracle(oracle_built, n, T, wev, cfg):
+    """After the reference's allocator unit test (tests/dymelor.c): random malloc / calloc / realloc / free over a set of
+    bins in the LP's rollbackable heap, every block pattern-checked before it is touched again, under thousands of
+    rollbacks.  First 36 state bytes: ops, failures (must be 0), hash of everything read back, live bytes, call counts."""
+    import struct
+    rows, st = run_emu("heapstress", n, T, wev, state_bytes=36, arena_bytes=1 << 15, bucket_width=0.5, n_buckets=1024, **cfg)
+    _, orows, _ = rs_trace.run_oracle("heapstress", n, sim_time=T, horizon=T, state_bytes=36)
+    assert rs_trace.compare(rows, orows) == []
+    assert st.rollbacks > 0
+    tot = [sum(struct.unpack("<IIQIIIII", r[4])[i] for r in rows) for i in range(8)]
+    assert tot[1] == 0 and min(tot[4:8]) > 1000         # no failed check; mallocs, callocs, reallocs and frees all happened

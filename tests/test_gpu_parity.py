@@ -320,3 +320,15 @@ def test_small_reference_models_vs_oracle(oracle_built, model, n, T, wev):
     _, orows, _ = rs_trace.run_oracle(model, n, sim_time=T, horizon=T, state_bytes=4)
     assert rs_trace.compare(rows, orows) == []
     assert st.committed_events == sum(r[0] for r in orows)
+
+
+@pytest.mark.parametrize("n,T,wev,cfg", [(200, 300, 4096, {}), (20000, 60, 1 << 18, {}), (50, 3000, 512, dict(ckpt_period=1))])
+def test_heap_stress_vs_oracle(oracle_built, n, T, wev, cfg):
+    """After the reference's allocator unit test (tests/dymelor.c): random malloc / calloc / realloc / free in the LP's
+    rollbackable heap with pattern checks, under rollbacks (tests/models/heapstress).  Bit-exact, no failed check."""
+    import struct
+    need("heapstress", oracle_built)
+    rows, st = run_gpu("heapstress", n, T, state_bytes=36, window_events=wev, arena_bytes=1 << 15, bucket_width=0.5, n_buckets=1024, **cfg)
+    _, orows, _ = rs_trace.run_oracle("heapstress", n, sim_time=T, horizon=T, state_bytes=36)
+    assert rs_trace.compare(rows, orows) == []
+    assert sum(struct.unpack("<IIQIIIII", r[4])[1] for r in rows) == 0
