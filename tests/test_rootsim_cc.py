@@ -99,3 +99,11 @@ def test_compile_only_objects_name_their_source(tmp_path, monkeypatch):
     assert (tmp_path / "b.o").read_text().split() == [cc.STUB_MAGIC, str(tmp_path / "b.c")]
     (tmp_path / "foreign.o").write_bytes(b"\x7fELF....")
     assert cc.main(["-o", "model", "foreign.o"]) == 1
+
+
+def test_unsupported_api_is_named():
+    """ABM layer and costs/probabilities topology entries are declarations only: the wrapper says
+    which one a model uses instead of leaving the user with a mangled name from the device linker."""
+    cc = load_cc()
+    src = "void f(void) { agent_t a = SpawnAgent(8); double v = GetValueTopology(0, 1); /* KillAgent(a) */ unsigned r = FindReceiver(); }\n"
+    assert [nm for _, nm in cc.unsupported_api([src])] == ["GetValueTopology", "SpawnAgent"]
