@@ -517,3 +517,29 @@ def test_heap_stress_emu_vs_oracle(oracle_built, n, T, wev, cfg):
     assert st.rollbacks > 0
     tot = [sum(struct.unpack("<IIQIIIII", r[4])[i] for r in rows) for i in range(8)]
     assert tot[1] == 0 and min(tot[4:8]) > 1000         # no failed check; mallocs, callocs, reallocs and frees all happened
+
+
+def test_traffic_randomized_configurations_emu(oracle_built):
+    """Eight seeded random draws of (grid, horizon, master seed, window size, bucket width, checkpoint period): the
+    committed trace is the oracle's whatever the window partition and the checkpoint spacing (zero-delay hand-offs
+    between neighbours, 16-byte payloads, up to 100,000 rollbacks in the larger draws of the same generator)."""
+    import random
+    if not rs_host.model_sources("traffic") or not os.path.exists(os.path.join(oracle_built, "seqp_traffic")):
+        pytest.skip("traffic sources live in the reference tree")
+    rng = random.Random(7)
+    lib = rs_host.build_model("traffic", emu=True)
+    for _ in range(8):
+        name = rng.choice(["traffic_grid_lp16", "traffic_grid_lp960"])
+        T = rng.choice([1000, 2000]) if name != "traffic_grid_lp16" else rng.choice([20000, 40000])
+        seed = rng.getrandbits(62) | 1
+        wev, bw, p = rng.choice([64, 512, 4096, 1 << 16, 1 << 20]), rng.choice([0.25, 1.0, 4.0, 16.0]), rng.choice([1, 3, 10, 1000])
+        text, n = traffic_topology(name)
+        _, orows, _ = rs_trace.run_oracle("traffic", n, sim_time=T, horizon=T, seed=seed, files={"topology.txt": text})
+        with rs_host.Engine(lib) as eng:
+            eng.model_file("topology.txt", text.encode())
+            eng.init(n_lps=n, master_seed=seed, simulation_time=float(T), window_events=wev, arena_bytes=1 << 17, max_payload=16,
+                     bucket_width=bw, n_buckets=4096, ckpt_period=p)
+            assert eng.run()
+            rows = rs_trace.engine_rows(eng, 8)
+            eng.model_file("topology.txt", None)
+        assert rs_trace.compare(rows, orows) == [], (name, T, seed, wev, bw, p)
