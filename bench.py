@@ -485,7 +485,13 @@ def traffic_block(rs_host, rs_trace):
         committed = st.committed_events - n
         v = committed / st.device_seconds
         if best is None or v > best["value"]:
+            # B_alg = E + f*E + 2*S + S/P + f*H, E = 32-byte record + 16-byte payload slot, f = records
+            # sent per committed event (measured), S = measured average checkpoint size, P = 10 (default --p), H = 16
+            S = st.checkpoint_bytes / max(1, st.checkpoints)
+            f = st.sent_records / max(1, committed)
+            b_alg = 48.0 + f * 48.0 + 2.0 * S + S / 10.0 + f * 16.0
             best = {"value": v, "committed_events": committed, "device_s": st.device_seconds, "init_s_incl_file_parse_on_device": t_init,
+                    "sends_per_event": f, "algorithmic_bytes_per_event": b_alg, "hbm_frac_whole_loop": b_alg * v / 1e9 / measured_peak()[0],
                     "e2e_value": committed / (time.time() - t0), "windows": st.windows, "rounds": st.relax_rounds,
                     "rollbacks": st.rollbacks, "silent_events": st.silent_events, "checkpoints": st.checkpoints,
                     "avg_checkpoint_bytes": st.checkpoint_bytes / max(1, st.checkpoints), "kernel_launches": st.kernel_launches}
