@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Golden checksums of the configurations bench.py times (BASELINE.json configs[1] and configs[3]).
+"""Golden checksums of the configurations bench.py times (BASELINE.json configs[1], [2], [3] and [4]).
 
 Runs the CPU oracle oracle/_build/seqp_phold (rs_math.h log: bit-identical with the device build) on the
 exact bench configuration and stores the order-independent checksum of the per-LP committed-trace digests
@@ -10,6 +10,7 @@ the device engine's digests in its end-to-end steps, at every GPU count, and fai
   python tests/golden/make_checksums.py 16777216 60     # 16,777,216 LPs, T=60  (~25 min, 30 GB)
   python tests/golden/make_checksums.py 65536 400 - pcs # models/pcs, 65,536 cells, T=400 (BASELINE configs[2], ~7 min)
   python tests/golden/make_checksums.py 4096 3600 - traffic  # models/traffic on the 4096-LP road grid, one simulated hour
+  python tests/golden/make_checksums.py 68608 3600 - traffic # ... on the 68,608-LP grid (BASELINE configs[4]; ~8 min, INIT is O(LPs x file))
 """
 import json
 import os
