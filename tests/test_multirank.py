@@ -115,3 +115,22 @@ def test_traffic_multirank_vs_oracle(oracle_built, tmp_path, world, name, T):
     _, orows, _ = rs_trace.run_oracle("traffic", n, sim_time=T, horizon=T, files={"topology.txt": text})
     assert rs_trace.compare(rows, orows) == []
     assert sum(g["stats"]["committed_events"] for g in got) == sum(r[0] for r in orows)
+
+
+@pytest.mark.parametrize("world,hot,chunk", [(2, 8, 16), (3, 32, 0)])
+def test_phold_multirank_with_chain_lps(oracle_built, tmp_path, world, hot, chunk):
+    """hot_threshold on several ranks: LPs with big groups become chain LPs (a warp of their own, a visit
+    budget per round) on every rank, and nothing they were due to execute may be dropped at the window commit."""
+    if not rs_host.model_sources("phold") or not os.path.exists(os.path.join(oracle_built, "seqp_phold")):
+        pytest.skip("phold sources live in the reference tree")
+    rs_host.build_model("phold", emu=True)
+    n, T = 300, 90
+    cfg = dict(master_seed=rs_trace.MASTER_SEED, simulation_time=float(T), window_events=1 << 20, arena_bytes=128, hot_threshold=hot,
+               bucket_width=0.25)
+    if chunk:
+        cfg["chunk_events"] = chunk
+    rows, got = run_ranks(world, {"model": "phold", "n": n, "state_bytes": 8, "cfg": cfg}, tmp_path)
+    _, orows, _ = rs_trace.run_oracle("phold", n, sim_time=T, horizon=T)
+    assert rs_trace.compare(rows, orows, state_mask=[0, 4, 5, 6, 7]) == []
+    assert sum(g["stats"]["committed_events"] for g in got) == sum(r[0] for r in orows)
+    assert sum(g["stats"]["chain_events"] for g in got) > 0
