@@ -543,3 +543,35 @@ def test_traffic_randomized_configurations_emu(oracle_built):
             rows = rs_trace.engine_rows(eng, 8)
             eng.model_file("topology.txt", None)
         assert rs_trace.compare(rows, orows) == [], (name, T, seed, wev, bw, p)
+
+
+def test_traffic_ragged_topology_file(oracle_built):
+    """A topology file with blank lines, comments between the data lines and NO trailing newline: the model strips the
+    last character of every line it reads (models/traffic/init.c:44,302), so the last segment loses its length, gets
+    zero queue slots and answers every arrival with "Object queue full" -- on the device exactly as in the reference."""
+    from conftest import have_reference_binary
+    if not rs_host.model_sources("traffic") or not os.path.exists(os.path.join(oracle_built, "seqp_traffic")):
+        pytest.skip("traffic sources live in the reference tree")
+    text, n = traffic_topology("traffic_grid_lp16")
+    out = []
+    for i, line in enumerate(text.rstrip("\n").split("\n")):
+        out.append(line)
+        if i % 5 == 2:
+            out += ["", "# a comment, with, commas"]
+    ragged = "\n".join(out)
+    T = 20000
+    lib = rs_host.build_model("traffic", emu=True)
+    with rs_host.Engine(lib) as eng:
+        eng.model_file("topology.txt", ragged.encode())
+        eng.init(n_lps=n, master_seed=rs_trace.MASTER_SEED, simulation_time=float(T), window_events=4096, arena_bytes=1 << 17,
+                 max_payload=16, bucket_width=4.0, n_buckets=4096)
+        assert eng.run()
+        rows = rs_trace.engine_rows(eng, 8)
+        eng.model_file("topology.txt", None)
+    _, orows, so = rs_trace.run_oracle("traffic", n, sim_time=T, horizon=T, files={"topology.txt": ragged})
+    assert rs_trace.compare(rows, orows) == []
+    assert so.count("Object queue full") > 100
+    if have_reference_binary("traffic"):
+        _, lrows, _ = rs_trace.run_oracle("traffic", n, sim_time=T, horizon=T, files={"topology.txt": ragged}, portable=False)
+        _, rrows, _ = rs_trace.run_reference("traffic", n, sim_time=T, horizon=T, files={"topology.txt": ragged})
+        assert rs_trace.compare(lrows, rrows) == []
